@@ -1,0 +1,3 @@
+class TimeLimit:
+    def __init__(self, env, max_episode_steps=None):
+        self.env = env
