@@ -1,0 +1,464 @@
+// CEM / iCEM population kernels: sampling, elite selection (radix select), refit, warm-start shift.
+//
+// Reference semantics (mbrl/planning/trajectory_opt.py):
+//   CEMOptimizer._sample_population 110-128, _update_population_params 130-140, optimize 142-188
+//   ICEMOptimizer.optimize 391-487;  util.math.truncated_normal_ util/math.py:69-92,
+//   powerlaw_psd_gaussian util/math.py:318-396;  TrajectoryOptimizer.optimize 563-567.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// sampling
+// ------------------------------------------------------------------------------------------------------
+__global__ void cem_sample_kernel(int n, int dims, const float* __restrict__ mu, const float* __restrict__ disp,
+                                  const float* __restrict__ lb, const float* __restrict__ ub,
+                                  const float* __restrict__ z, unsigned long long seed, unsigned long long offset,
+                                  int clipped, float* __restrict__ pop) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * dims) return;
+  const int d = (int)(idx % dims);
+  const float m = mu[d], dp = disp[d], lo = lb[d], hi = ub[d];
+  float zz;
+  if (z) {
+    zz = z[idx];
+  } else {
+    // N(0,1); truncated to [-2, 2] by redrawing violators (util/math.py:83-92) unless clipped_normal
+    uint32_t attempt = 0;
+    const int n_i = (int)(idx / dims);
+    while (true) {
+      float g[4];
+      philox_normal4((uint32_t)n_i, (uint32_t)(d >> 2), RNG_STREAM_CEM | attempt, (uint32_t)offset, seed, g);
+      zz = g[d & 3];
+      if (clipped || (zz >= -2.0f && zz <= 2.0f) || attempt >= 64) break;
+      ++attempt;
+    }
+    if (!clipped) zz = fminf(fmaxf(zz, -2.0f), 2.0f);
+  }
+  float v;
+  if (clipped) {  // trajectory_opt.py:116-120 (dispersion is a standard deviation)
+    v = m + dp * zz;
+    v = v > lo ? v : lo;
+    v = v < hi ? v : hi;
+  } else {        // trajectory_opt.py:122-128 (dispersion is a variance)
+    const float l2 = (m - lo) / 2.0f, u2 = (hi - m) / 2.0f;
+    const float mv = fminf(l2 * l2, u2 * u2);
+    const float cv = fminf(mv, dp);
+    v = zz * sqrtf(cv) + m;
+  }
+  pop[idx] = v;
+}
+
+// iCEM coloured noise: one thread per (sequence, action dim) synthesises the H samples of its series
+__global__ void icem_sample_kernel(int n, int H, int A, float exponent, const float* __restrict__ mu,
+                                   const float* __restrict__ var, const float* __restrict__ lb,
+                                   const float* __restrict__ ub, const float* __restrict__ sr,
+                                   const float* __restrict__ si, unsigned long long seed, unsigned long long offset,
+                                   float* __restrict__ pop) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * A) return;
+  const int ni = (int)(idx / A), ad = (int)(idx % A);
+  const int K = H / 2 + 1;
+  // spectrum scale s_k = f_k^(-beta/2), f_0 := f_1 (low-frequency cut-off 1/H); theoretical sigma
+  float sig2 = 0.f;
+  for (int k = 1; k < K; ++k) {
+    float w = powf((float)k / (float)H, -exponent / 2.0f);
+    if (k == K - 1) w *= (1.0f + (float)(H % 2)) / 2.0f;
+    sig2 += w * w;
+  }
+  const float sigma = 2.0f * sqrtf(sig2) / (float)H;
+  for (int t = 0; t < H; ++t) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float s = powf((float)(k == 0 ? 1 : k) / (float)H, -exponent / 2.0f);
+      float zr, zi;
+      if (sr) {
+        zr = sr[((size_t)ni * A + ad) * K + k];
+        zi = si[((size_t)ni * A + ad) * K + k];
+      } else {
+        float g[4];
+        philox_normal4((uint32_t)ni, (uint32_t)(ad * K + k), RNG_STREAM_ICEM, (uint32_t)offset, seed, g);
+        zr = g[0];
+        zi = g[1];
+      }
+      const float re = zr * s;
+      float im = zi * s;
+      const bool nyq = (H % 2 == 0) && (k == K - 1);
+      if (k == 0 || nyq) im = 0.f;
+      const int ph = (int)(((long long)k * t) % H);
+      float sn, cs;
+      sincospif(2.0f * (float)ph / (float)H, &sn, &cs);
+      const float term = re * cs - im * sn;
+      acc += (k == 0 || nyq) ? term : 2.0f * term;
+    }
+    const float y = acc / (float)H / sigma;
+    const int d = t * A + ad;
+    float v = fminf(y * sqrtf(var[d]) + mu[d], ub[d]);
+    v = fmaxf(v, lb[d]);
+    pop[((size_t)ni * H + t) * A + ad] = v;
+  }
+}
+
+__global__ void icem_append_kernel(int keep, int H, int A, const float* __restrict__ elite,
+                                   const long long* __restrict__ index, int shift, const float* __restrict__ mu,
+                                   const float* __restrict__ var, const float* __restrict__ end_eps,
+                                   unsigned long long seed, unsigned long long offset, float* __restrict__ dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= keep * H * A) return;
+  const int j = idx / (H * A), t = (idx / A) % H, ad = idx % A;
+  const long long src = index ? index[j] : j;
+  float v;
+  if (!shift) {
+    v = elite[(src * H + t) * A + ad];
+  } else if (t < H - 1) {
+    v = elite[(src * H + t + 1) * A + ad];
+  } else {  // trajectory_opt.py:451-459: fresh last action ~ N(mu[-1], sqrt(var[-1]))
+    float e;
+    if (end_eps) {
+      e = end_eps[j * A + ad];
+    } else {
+      float g[4];
+      philox_normal4((uint32_t)j, (uint32_t)(ad >> 2), RNG_STREAM_ICEM | 1u, (uint32_t)offset, seed, g);
+      e = g[ad & 3];
+    }
+    v = mu[(H - 1) * A + ad] + sqrtf(var[(H - 1) * A + ad]) * e;
+  }
+  dst[idx] = v;
+}
+
+__global__ void shift_kernel(int H, int A, int replan, const float* __restrict__ best,
+                             const float* __restrict__ init_row, float* __restrict__ prev) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * A) return;
+  const int t = idx / A, ad = idx % A;
+  prev[idx] = (t < H - replan) ? best[(t + replan) * A + ad] : init_row[ad];
+}
+
+// mean over particles of the per-row returns: model_env.py:190-191
+__global__ void particle_mean_kernel(int N, int P, const float* __restrict__ total, float* __restrict__ returns) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += total[(size_t)n * P + p];
+  returns[n] = s / (float)P;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// elite selection + refit: one CTA
+// ------------------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 1024;
+
+__device__ __forceinline__ uint32_t order_key(float v) {
+  uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += n;
+    }
+    warp_sums[lane] = winc - w;
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  int res = warp_sums[warp] + inc - v;
+  __syncthreads();
+  return res;
+}
+
+struct SelArgs {
+  int n, dims, k;
+  float alpha;
+  int unbiased, use_std;
+  int mode;  // 0: refit in place, 1: emit top-k records only
+  const float* pop;
+  long long pstride;
+  float* values;
+  long long vstride;
+  float* mu;
+  float* disp;
+  float* best_value;
+  float* best_solution;
+  int* elite_idx;
+  float* elites_out;
+  float* records;
+  float* partial;  // [32][dims] scratch
+};
+
+__global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArgs s) {
+  __shared__ int hist[256];
+  __shared__ int warp_sums[32];
+  __shared__ int sh_total;
+  __shared__ uint32_t sh_prefix;
+  __shared__ int sh_krem;
+  __shared__ float sh_bestv[32];
+  __shared__ int sh_besti[32];
+  const int tid = threadIdx.x;
+  const int n = s.n, k = s.k;
+
+  // NaN -> -1e-10 (trajectory_opt.py:178), in place like the reference
+  for (int i = tid; i < n; i += kSelThreads) {
+    float v = s.values[i * s.vstride];
+    if (isnan(v)) s.values[i * s.vstride] = -1e-10f;
+  }
+  if (tid == 0) {
+    sh_prefix = 0;
+    sh_krem = k;
+  }
+  __syncthreads();
+
+  // ---- radix select of the k-th largest key, most significant byte first ----
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int b = tid; b < 256; b += kSelThreads) hist[b] = 0;
+    __syncthreads();
+    const uint32_t prefix = sh_prefix;
+    const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = tid; i < n; i += kSelThreads) {
+      uint32_t key = order_key(s.values[i * s.vstride]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int krem = sh_krem, cum = 0, d = 255;
+      for (; d > 0; --d) {
+        if (cum + hist[d] >= krem) break;
+        cum += hist[d];
+      }
+      sh_krem = krem - cum;
+      sh_prefix = prefix | ((uint32_t)d << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t T = sh_prefix;  // key of the k-th largest value
+  const int need_eq = sh_krem;   // how many elements equal to T belong to the top-k (lowest indices first)
+
+  // ---- ordered compaction of the selected indices ----
+  int base_sel = 0, base_eq = 0;
+  for (int c0 = 0; c0 < n; c0 += kSelThreads) {
+    const int i = c0 + tid;
+    uint32_t key = i < n ? order_key(s.values[i * s.vstride]) : 0u;
+    const int gt = (i < n && key > T) ? 1 : 0;
+    const int eq = (i < n && key == T) ? 1 : 0;
+    int tot_eq;
+    const int eq_rank = block_exclusive_scan(eq, warp_sums, &sh_total);
+    tot_eq = sh_total;
+    const int sel = gt | (eq && (base_eq + eq_rank) < need_eq ? 1 : 0);
+    const int pos = block_exclusive_scan(sel, warp_sums, &sh_total);
+    const int tot_sel = sh_total;
+    if (sel) s.elite_idx[base_sel + pos] = i;
+    base_sel += tot_sel;
+    base_eq += tot_eq;
+    __syncthreads();
+  }
+
+  // ---- best value: max, lowest index on ties (best_values[0] / elite_idx[0] of topk) ----
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < n; i += kSelThreads) {
+    float v = s.values[i * s.vstride];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((tid & 31) == 0) { sh_bestv[tid >> 5] = bv; sh_besti[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid < 32) {
+    bv = sh_bestv[tid];
+    bi = sh_besti[tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (tid == 0) { sh_bestv[0] = bv; sh_besti[0] = bi; }
+  }
+  __syncthreads();
+  bv = sh_bestv[0];
+  bi = sh_besti[0];
+
+  if (s.mode == 1) {  // records [k][1 + dims]
+    for (int idx = tid; idx < k * (s.dims + 1); idx += kSelThreads) {
+      const int j = idx / (s.dims + 1), c = idx % (s.dims + 1);
+      const int src = s.elite_idx[j];
+      s.records[idx] = c == 0 ? s.values[src * s.vstride] : s.pop[src * s.pstride + (c - 1)];
+    }
+    return;
+  }
+
+  // ---- mean / variance over the elites: warps split the elite list, lanes stride the coordinates ----
+  const int warp = tid >> 5, lane = tid & 31;
+  const int dims = s.dims;
+  for (int d = lane; d < dims; d += 32) {
+    float acc = 0.f;
+    for (int e = warp; e < k; e += 32) acc += s.pop[s.elite_idx[e] * s.pstride + d];
+    s.partial[warp * dims + d] = acc;
+  }
+  __syncthreads();
+  for (int d = tid; d < dims; d += kSelThreads) {
+    float acc = 0.f;
+    for (int w = 0; w < 32; ++w) acc += s.partial[w * dims + d];
+    s.partial[32 * dims + d] = acc / (float)k;  // mean
+  }
+  __syncthreads();
+  for (int d = lane; d < dims; d += 32) {
+    const float mean = s.partial[32 * dims + d];
+    float acc = 0.f;
+    for (int e = warp; e < k; e += 32) {
+      float df = s.pop[s.elite_idx[e] * s.pstride + d] - mean;
+      acc += df * df;
+    }
+    s.partial[warp * dims + d] = acc;
+  }
+  __syncthreads();
+  for (int d = tid; d < dims; d += kSelThreads) {
+    float acc = 0.f;
+    for (int w = 0; w < 32; ++w) acc += s.partial[w * dims + d];
+    const float mean = s.partial[32 * dims + d];
+    float var = acc / (float)(s.unbiased ? (k - 1) : k);
+    float nd = s.use_std ? sqrtf(var) : var;
+    s.mu[d] = s.alpha * s.mu[d] + (1.0f - s.alpha) * mean;
+    s.disp[d] = s.alpha * s.disp[d] + (1.0f - s.alpha) * nd;
+  }
+  if (s.elites_out) {
+    for (int idx = tid; idx < k * dims; idx += kSelThreads) {
+      const int j = idx / dims, d = idx % dims;
+      s.elites_out[idx] = s.pop[s.elite_idx[j] * s.pstride + d];
+    }
+  }
+  // ---- best-so-far (trajectory_opt.py:184-186) ----
+  const bool better = bv > *s.best_value;
+  __syncthreads();
+  if (better) {
+    for (int d = tid; d < dims; d += kSelThreads) s.best_solution[d] = s.pop[bi * s.pstride + d];
+    if (tid == 0) *s.best_value = bv;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200pets_cem_sample(int32_t population, int32_t dims, const float* mu, const float* dispersion,
+                        const float* lower, const float* upper, const float* z, uint64_t seed, uint64_t offset,
+                        int32_t clipped_normal, float* population_out, void* stream) {
+  if (population <= 0 || dims <= 0) return b200pets_set_error(B200PETS_EINVAL, "cem_sample: empty population");
+  long long tot = (long long)population * dims;
+  cem_sample_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      population, dims, mu, dispersion, lower, upper, z, seed, offset, clipped_normal, population_out);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}
+
+size_t b200pets_cem_update_workspace_bytes(int32_t population, int32_t dims, int32_t elite_num) {
+  (void)population;
+  return (size_t)33 * dims * sizeof(float) + (size_t)elite_num * sizeof(int32_t) + 256;
+}
+
+static int run_select(int mode, int n, int dims, int k, float alpha, int unbiased, int use_std, const float* pop,
+                      long long pstride, float* values, long long vstride, float* mu, float* disp, float* best_value,
+                      float* best_solution, int32_t* elite_idx, float* elites_out, float* records, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (n <= 0 || dims <= 0 || k <= 0 || k > n)
+    return b200pets_set_error(B200PETS_EINVAL, "cem_update: need 0 < elite_num (%d) <= population (%d)", k, n);
+  if (mode == 0 && unbiased && k < 2)
+    return b200pets_set_error(B200PETS_EINVAL, "cem_update: unbiased variance needs at least 2 elites");
+  size_t need = b200pets_cem_update_workspace_bytes(n, dims, k);
+  if (workspace_bytes < need) return b200pets_set_error(B200PETS_EINVAL, "cem_update: workspace too small (%zu < %zu)", workspace_bytes, need);
+  SelArgs s{};
+  s.n = n; s.dims = dims; s.k = k; s.alpha = alpha; s.unbiased = unbiased; s.use_std = use_std; s.mode = mode;
+  s.pop = pop; s.pstride = pstride; s.values = values; s.vstride = vstride; s.mu = mu; s.disp = disp;
+  s.best_value = best_value; s.best_solution = best_solution; s.elites_out = elites_out; s.records = records;
+  s.partial = reinterpret_cast<float*>(workspace);
+  s.elite_idx = elite_idx ? elite_idx : reinterpret_cast<int*>(reinterpret_cast<float*>(workspace) + 33 * (size_t)dims);
+  cem_select_kernel<<<1, kSelThreads, 0, (cudaStream_t)stream>>>(s);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}
+
+int b200pets_cem_update(int32_t population, int32_t dims, int32_t elite_num, float alpha, int32_t unbiased,
+                        int32_t use_std, const float* population_in, float* values, float* mu, float* dispersion,
+                        float* best_value, float* best_solution, int32_t* elite_idx, float* elites_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  return run_select(0, population, dims, elite_num, alpha, unbiased, use_std, population_in, dims, values, 1, mu,
+                    dispersion, best_value, best_solution, elite_idx, elites_out, nullptr, workspace, workspace_bytes,
+                    stream);
+}
+
+int b200pets_cem_local_topk(int32_t population, int32_t dims, int32_t k, const float* population_in, float* values,
+                            float* records, void* workspace, size_t workspace_bytes, void* stream) {
+  return run_select(1, population, dims, k, 0.f, 0, 0, population_in, dims, values, 1, nullptr, nullptr, nullptr,
+                    nullptr, nullptr, nullptr, records, workspace, workspace_bytes, stream);
+}
+
+int b200pets_cem_update_from_records(int32_t num_records, int32_t dims, int32_t elite_num, float alpha,
+                                     int32_t unbiased, int32_t use_std, float* records, float* mu, float* dispersion,
+                                     float* best_value, float* best_solution, float* elites_out, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  return run_select(0, num_records, dims, elite_num, alpha, unbiased, use_std, records + 1, dims + 1, records,
+                    dims + 1, mu, dispersion, best_value, best_solution, nullptr, elites_out, nullptr, workspace,
+                    workspace_bytes, stream);
+}
+
+int b200pets_icem_sample(int32_t n, int32_t horizon, int32_t act_dim, float exponent, const float* mu,
+                         const float* var, const float* lower, const float* upper, const float* sr, const float* si,
+                         uint64_t seed, uint64_t offset, float* population_out, void* stream) {
+  if (n <= 0 || horizon <= 0 || act_dim <= 0) return b200pets_set_error(B200PETS_EINVAL, "icem_sample: empty population");
+  if ((sr == nullptr) != (si == nullptr)) return b200pets_set_error(B200PETS_EINVAL, "icem_sample: sr and si go together");
+  long long tot = (long long)n * act_dim;
+  icem_sample_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      n, horizon, act_dim, exponent, mu, var, lower, upper, sr, si, seed, offset, population_out);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}
+
+int b200pets_icem_append_elites(int32_t keep, int32_t horizon, int32_t act_dim, const float* elite,
+                                const int64_t* index, int32_t shift, const float* mu, const float* var,
+                                const float* end_eps, uint64_t seed, uint64_t offset, float* dst, void* stream) {
+  if (keep <= 0) return B200PETS_OK;
+  int tot = keep * horizon * act_dim;
+  icem_append_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      keep, horizon, act_dim, elite, reinterpret_cast<const long long*>(index), shift, mu, var, end_eps, seed, offset, dst);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}
+
+int b200pets_shift_solution(int32_t horizon, int32_t act_dim, int32_t replan_freq, const float* best,
+                            const float* initial_row, float* previous_solution, void* stream) {
+  if (replan_freq < 0 || replan_freq > horizon) return b200pets_set_error(B200PETS_EINVAL, "shift: replan_freq out of range");
+  int tot = horizon * act_dim;
+  shift_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(horizon, act_dim, replan_freq, best, initial_row,
+                                                                    previous_solution);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}
+
+}  // extern "C"
+
+int launch_particle_mean(int N, int P, const float* total, float* returns, cudaStream_t stream) {
+  particle_mean_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, P, total, returns);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}

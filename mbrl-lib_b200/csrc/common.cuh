@@ -1,0 +1,236 @@
+// Shared device-side definitions of the PETS planning kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200pets.h"
+
+#define B200PETS_MAX_LAYERS 8
+
+// Everything a rollout kernel needs to know about the staged model; passed by value (kernel parameter).
+struct ModelDev {
+  int E, M, D, A, Dp, in, out, hid, L;  // L = hidden layers; layers = L + 1
+  int nout;                             // width of the last layer: out (deterministic) or 2*out
+  int act;
+  float leaky;
+  int obs_process, learned_rewards, target_is_delta, deterministic, reward_fn, term_fn, norm_mode;
+  int K[B200PETS_MAX_LAYERS], N[B200PETS_MAX_LAYERS];
+  const float* W[B200PETS_MAX_LAYERS];  // gathered elite members: [M][K][N]
+  const float* b[B200PETS_MAX_LAYERS];  // [M][N]
+  const double* norm_mean_d;            // [in]
+  const double* norm_std_d;
+  const float* norm_mean_f;
+  const float* norm_std_f;
+  const float* norm_istd_f;             // 1/std in fp32 (tensor-core path)
+  const float* min_lv;                  // [out]
+  const float* max_lv;
+  const uint8_t* no_delta;              // [D] mask
+  // tensor-core images (bf16, UMMA no-swizzle K-major canonical layout), see rollout_tc.cu
+  const uint8_t* img;                   // base of member 0
+  uint32_t img_member_stride;           // bytes between members
+  uint32_t img_layer_off[B200PETS_MAX_LAYERS];
+  int Kp[B200PETS_MAX_LAYERS], Np[B200PETS_MAX_LAYERS];
+  int outp;                             // padded out (multiple of 16): logvar columns start here
+};
+
+// One launch of a rollout kernel: steps [t0, t1) of every tile.
+struct RolloutArgs {
+  int N, H, P;          // population, horizon (stride of the action tensor), particles
+  long long B;          // rows
+  int t0, t1;
+  int propagation;      // B200PETS_PROP_*
+  int slot_mode;        // 0: rid = perm[slot] (or slot if perm == NULL), members own contiguous slot ranges
+                        // 1: tile shuffle: rid = (slot % N) * P + slot / N, member drawn per (tile, step)
+                        // 2: as 1 but the member is drawn once per tile (TSinf without an injected permutation)
+  const long long* perm;   // [B] for this launch or NULL
+  const float* eps;        // [t1-t0][B][out] for this launch (row-id indexed) or NULL -> Philox
+  int sample;              // 0: mean prediction
+  unsigned long long seed, offset;
+  // action source: act + (rid / act_div) * act_row_stride + t * act_t_stride
+  const float* act;
+  long long act_row_stride;
+  int act_div, act_t_stride;
+  // state
+  const float* obs0;       // [D] broadcast initial state (used when init_from_obs0)
+  int init_from_obs0;
+  const float* obs_in;     // [B][D] gather source when !init_from_obs0
+  float* obs_out;          // [B][D] scatter target (NULL when the state is not needed after the launch)
+  float* total_state;      // [B]
+  uint8_t* dead_state;     // [B]
+  int load_state, store_state;
+  // step outputs (b200pets_step): next_obs = obs_out, reward, done
+  float* reward_out;       // [B] or NULL
+  uint8_t* done_out;       // [B] or NULL
+};
+
+// ------------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (Salmon et al. 2011).  key = seed, counter = (a, b, c, d).
+// ------------------------------------------------------------------------------------------------------
+struct U4 {
+  uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                            uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return U4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0, 1)
+  return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+// four N(0,1) draws from one Philox block
+__device__ __forceinline__ void philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               unsigned long long seed, float out[4]) {
+  U4 r = philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  float u0 = u32_to_unit(r.x), u1 = u32_to_unit(r.y), u2 = u32_to_unit(r.z), u3 = u32_to_unit(r.w);
+  float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+  float s0, c0f, s1, c1f;
+  __sincosf(6.283185307179586f * u1, &s0, &c0f);
+  __sincosf(6.283185307179586f * u3, &s1, &c1f);
+  out[0] = r0 * c0f; out[1] = r0 * s0; out[2] = r1 * c1f; out[3] = r1 * s1;
+}
+
+// RNG stream tags (third counter word, high bits)
+#define RNG_STREAM_EPS 0x10000u
+#define RNG_STREAM_MEMBER 0x20000u
+#define RNG_STREAM_CEM 0x30000u
+#define RNG_STREAM_ICEM 0x40000u
+#define RNG_STREAM_PERM 0x50000u
+
+// ------------------------------------------------------------------------------------------------------
+// small math
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_f(float x) {  // torch F.softplus (beta 1, threshold 20)
+  return x > 20.0f ? x : log1pf(expf(x));
+}
+
+__device__ __forceinline__ float activation_f(float x, int act, float slope) {
+  if (act == B200PETS_ACT_SILU) return x / (1.0f + expf(-x));
+  if (act == B200PETS_ACT_RELU) return fmaxf(x, 0.0f);
+  return x > 0.0f ? x : x * slope;
+}
+
+// processed observation element j of the model input (obs_process_fn), obs points at one row [D]
+__device__ __forceinline__ float proc_obs_elem(const float* obs, int j, int mode, int stride = 1) {
+  if (mode == B200PETS_PROC_NONE) return obs[j * stride];
+  if (mode == B200PETS_PROC_HALFCHEETAH) {  // [o1, sin o2, cos o2, o3:]  (D -> D)
+    if (j == 0) return obs[1 * stride];
+    if (j == 1) return sinf(obs[2 * stride]);
+    if (j == 2) return cosf(obs[2 * stride]);
+    return obs[j * stride];
+  }
+  // cartpole: [sin o1, cos o1, o0, o2:]  (D -> D + 1)
+  if (j == 0) return sinf(obs[1 * stride]);
+  if (j == 1) return cosf(obs[1 * stride]);
+  if (j == 2) return obs[0];
+  return obs[(j - 1) * stride];
+}
+
+// reward_fn(act, next_obs) -- mbrl/env/reward_fns.py
+__device__ __forceinline__ bool term_eval(int fn, const float* o, int D, int os);
+
+__device__ __forceinline__ float reward_eval(int fn, const float* a, int A, int as, const float* o, int D, int os) {
+  switch (fn) {
+    case B200PETS_REWARD_CARTPOLE:
+      return term_eval(B200PETS_TERM_CARTPOLE, o, D, os) ? 0.0f : 1.0f;
+    case B200PETS_REWARD_INVERTED_PENDULUM:
+      return term_eval(B200PETS_TERM_INVERTED_PENDULUM, o, D, os) ? 0.0f : 1.0f;
+    case B200PETS_REWARD_CARTPOLE_PETS: {
+      float x0 = o[0], th = o[os];
+      float ex = x0 - 0.6f * sinf(th) - 0.0f, ey = -0.6f * cosf(th) - 0.6f;
+      float obs_cost = expf(-(ex * ex + ey * ey) / (0.6f * 0.6f));
+      float s = 0.f;
+      for (int i = 0; i < A; ++i) s += a[i * as] * a[i * as];
+      return obs_cost + (-0.01f * s);
+    }
+    case B200PETS_REWARD_HALFCHEETAH: {
+      float s = 0.f;
+      for (int i = 0; i < A; ++i) s += a[i * as] * a[i * as];
+      float run = o[0] - 0.0f * (o[2 * os] * o[2 * os]);
+      return run + (-0.1f * s);
+    }
+    case B200PETS_REWARD_PUSHER: {
+      const float g[3] = {0.45f, -0.05f, -0.323f};
+      float d1 = 0.f, d2 = 0.f;
+      for (int i = 0; i < 3; ++i) {
+        d1 += fabsf(o[(14 + i) * os] - o[(17 + i) * os]);
+        d2 += fabsf(g[i] - o[(17 + i) * os]);
+      }
+      float s = 0.f;
+      for (int i = 0; i < A; ++i) s += a[i * as] * a[i * as];
+      return -((0.5f * d1 + 1.25f * d2) + 0.1f * s);
+    }
+    default:
+      return 0.0f;
+  }
+}
+
+// termination_fn(act, next_obs) -- mbrl/env/termination_fns.py
+__device__ __forceinline__ bool term_eval(int fn, const float* o, int D, int os) {
+  switch (fn) {
+    case B200PETS_TERM_CARTPOLE: {
+      float x = o[0], th = o[2 * os];
+      const float lim = (float)(12.0 * 2.0 * 3.141592653589793 / 360.0);
+      bool ok = (x > -2.4f) && (x < 2.4f) && (th > -lim) && (th < lim);
+      return !ok;
+    }
+    case B200PETS_TERM_INVERTED_PENDULUM: {
+      bool fin = true;
+      for (int i = 0; i < D; ++i) fin = fin && isfinite(o[i * os]);
+      return !(fin && fabsf(o[os]) <= 0.2f);
+    }
+    case B200PETS_TERM_HOPPER: {
+      bool ok = true;
+      for (int i = 0; i < D; ++i) ok = ok && isfinite(o[i * os]);
+      for (int i = 1; i < D; ++i) ok = ok && (fabsf(o[i * os]) < 100.0f);
+      ok = ok && (o[0] > 0.7f) && (fabsf(o[os]) < 0.2f);
+      return !ok;
+    }
+    case B200PETS_TERM_WALKER2D: {
+      float h = o[0], an = o[os];
+      return !((h > 0.8f) && (h < 2.0f) && (an > -1.0f) && (an < 1.0f));
+    }
+    case B200PETS_TERM_ANT: {
+      bool fin = true;
+      for (int i = 0; i < D; ++i) fin = fin && isfinite(o[i * os]);
+      return !(fin && (o[0] >= 0.2f) && (o[0] <= 1.0f));
+    }
+    case B200PETS_TERM_HUMANOID:
+      return (o[0] < 1.0f) || (o[0] > 2.0f);
+    default:
+      return false;
+  }
+}
+
+// slot -> row id and tile -> member bookkeeping shared by both rollout kernels
+__device__ __forceinline__ long long slot_to_rid(const RolloutArgs& a, long long slot) {
+  if (a.slot_mode >= 1) return (slot % a.N) * (long long)a.P + slot / a.N;
+  return a.perm ? a.perm[slot] : slot;
+}
+
+__device__ __forceinline__ int shuffle_member(const RolloutArgs& a, int tile, int t, int M) {
+  if (a.slot_mode == 2) t = 0;
+  U4 r = philox4x32_10((uint32_t)tile, (uint32_t)t, RNG_STREAM_MEMBER, (uint32_t)a.offset, (uint32_t)a.seed,
+                       (uint32_t)(a.seed >> 32));
+  return (int)(((unsigned long long)r.x * (unsigned long long)M) >> 32);
+}
+
+// host-side error plumbing (api.cu)
+int b200pets_set_error(int code, const char* fmt, ...);
+#define CUDA_TRY(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return b200pets_set_error(B200PETS_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                __FILE__, __LINE__);                                              \
+  } while (0)

@@ -1,0 +1,199 @@
+"""``ModelEnv`` with the reference's interface (mbrl/models/model_env.py:15-191) over the CUDA rollout kernels.
+
+Drop-in: same constructor ``(env, model, termination_fn, reward_fn=None, generator=None)``, same
+``reset`` / ``step`` / ``evaluate_action_sequences`` signatures, shapes, return types and error behaviour.
+Extra keyword-only knobs choose the arithmetic (``precision``) and how TS1 draws members (``ts1``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, functions
+from .staging import StagedModel
+
+
+class ModelEnv:
+    def __init__(self, env, model, termination_fn, reward_fn=None, generator: Optional[torch.Generator] = None, *,
+                 precision: str = "auto", ts1: str = "tile_shuffle"):
+        self.dynamics_model = model
+        self.termination_fn = termination_fn
+        self.reward_fn = reward_fn
+        self.device = torch.device(model.device)
+        self.observation_space = env.observation_space
+        self.action_space = env.action_space
+        self._rng = generator if generator is not None else torch.Generator(device=self.device)
+        self._return_as_np = True
+        if ts1 not in ("tile_shuffle", "perms"):
+            raise ValueError("ts1 must be 'tile_shuffle' (in-kernel member draw) or 'perms' (torch.randperm per step)")
+        self.ts1 = ts1
+        self.lib = _lib.load()
+        self.staged = StagedModel(model, reward_fn, termination_fn)
+        if precision == "auto":
+            precision = "bf16_tc" if self.staged.supports_tc() else "f32"
+        self.precision = precision
+        self._seed = int(self._rng.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self._offset = 0
+        self._ws: Optional[torch.Tensor] = None
+        self._obs_pin: Optional[torch.Tensor] = None
+        self._obs_dev: Optional[torch.Tensor] = None
+
+    # ---- helpers ---------------------------------------------------------------------------------------
+    def _propagation(self) -> str:
+        pm = getattr(self.staged.mlp, "propagation_method", None)
+        if pm is None:
+            if len(self.staged.members()) == 1:
+                return "expectation"  # single model: plain forward
+            raise ValueError("ensemble models need a propagation_method for ModelEnv (gaussian_mlp.py:185-190)")
+        if pm not in _lib.PROP:
+            raise ValueError(f"Invalid propagation method {pm}.")  # gaussian_mlp.py:216
+        return pm
+
+    def _next_offset(self) -> int:
+        self._offset += 1
+        return self._offset
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _obs_to_device(self, initial_state: np.ndarray) -> torch.Tensor:
+        """host fp64/fp32 observation -> fp32 device vector through a pinned staging buffer."""
+        D = initial_state.shape[0]
+        if self._obs_pin is None or self._obs_pin.numel() != D:
+            self._obs_pin = torch.empty(D, dtype=torch.float32).pin_memory()
+            self._obs_dev = torch.empty(D, dtype=torch.float32, device=self.device)
+        self._obs_pin.copy_(torch.from_numpy(np.ascontiguousarray(initial_state, dtype=np.float32)))
+        self._obs_dev.copy_(self._obs_pin, non_blocking=True)
+        return self._obs_dev
+
+    # ---- reference API ---------------------------------------------------------------------------------
+    def reset(self, initial_obs_batch: np.ndarray, return_as_np: bool = True) -> Dict[str, torch.Tensor]:
+        assert len(initial_obs_batch.shape) == 2  # batch, obs_dim  (model_env.py:78-79)
+        self.staged.ensure_fresh()
+        obs = torch.from_numpy(np.ascontiguousarray(initial_obs_batch.astype(np.float32))).to(self.device)
+        state = {"obs": obs, "propagation_indices": None}
+        if self._propagation() == "fixed_model":
+            B, M = obs.shape[0], len(self.staged.members())
+            if B % M != 0:  # gaussian_mlp.py:369-373
+                raise ValueError("To use GaussianMLP's ensemble propagation, the batch size must "
+                                 "be a multiple of the number of models in the ensemble.")
+            state["propagation_indices"] = torch.randperm(B, device=self.device)
+        self._return_as_np = return_as_np
+        return state
+
+    def step(self, actions, model_state: Dict[str, torch.Tensor], sample: bool = False, *,
+             _perm: Optional[torch.Tensor] = None, _eps: Optional[torch.Tensor] = None):
+        assert len(actions.shape) == 2  # batch, action_dim  (model_env.py:108)
+        self.staged.ensure_fresh()
+        with torch.no_grad():
+            if isinstance(actions, np.ndarray):
+                actions = torch.from_numpy(actions).to(self.device)
+            actions = actions.to(torch.float32).contiguous()
+            obs = model_state["obs"]
+            if isinstance(obs, np.ndarray):
+                obs = torch.from_numpy(obs).to(self.device)
+            obs = obs.to(torch.float32).contiguous()
+            B = obs.shape[0]
+            prop = self._propagation()
+            perm = _perm
+            if perm is None:
+                if prop == "fixed_model":
+                    perm = model_state.get("propagation_indices")
+                    if perm is None:
+                        raise ValueError("When using propagation='fixed_model', `propagation_indices` must be provided.")
+                elif prop == "random_model" and self.ts1 == "perms":
+                    perm = torch.randperm(B, device=self.device)
+            if perm is not None:
+                perm = perm.to(torch.int64).contiguous()
+            d = self.staged.desc
+            next_obs = torch.empty_like(obs)
+            reward = torch.empty(B, dtype=torch.float32, device=self.device)
+            done = torch.empty(B, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.b200pets_step(
+                    self.staged.handle, _lib.PREC[self.precision], _lib.PROP[prop], B, _lib.ptr(obs), _lib.ptr(actions),
+                    _lib.ptr(perm), _lib.ptr(_eps), self._seed, self._next_offset(), int(bool(sample)), _lib.ptr(next_obs),
+                    _lib.ptr(reward), _lib.ptr(done), _lib.stream_ptr()), "step")
+            rewards = reward.view(-1, 1)
+            dones = done.view(-1, 1).bool()
+            if d.reward_fn == _lib.REWARD["external"]:
+                rewards = self.reward_fn(actions, next_obs)
+            if d.term_fn == _lib.TERM["external"]:
+                dones = self.termination_fn(actions, next_obs)
+            next_state = dict(model_state)
+            next_state["obs"] = next_obs
+            if self._return_as_np:
+                return next_obs.cpu().numpy(), rewards.cpu().numpy(), dones.cpu().numpy(), next_state
+            return next_obs, rewards, dones, next_state
+
+    def render(self, mode="human"):
+        pass
+
+    def evaluate_action_sequences(self, action_sequences: torch.Tensor, initial_state: np.ndarray, num_particles: int, *,
+                                  _perms: Optional[torch.Tensor] = None, _eps: Optional[torch.Tensor] = None,
+                                  _row_returns: Optional[torch.Tensor] = None) -> torch.Tensor:
+        with torch.no_grad():
+            assert len(action_sequences.shape) == 3  # model_env.py:166
+            population_size, horizon, action_dim = action_sequences.shape
+            assert initial_state.ndim in (1, 3)  # model_env.py:169
+            if initial_state.ndim != 1:
+                raise NotImplementedError("pixel observations are outside the GaussianMLP hot path")
+            self.staged.ensure_fresh()
+            d = self.staged.desc
+            if d.reward_fn == _lib.REWARD["external"] or d.term_fn == _lib.TERM["external"]:
+                return self._evaluate_stepwise(action_sequences, initial_state, num_particles)
+            actions = action_sequences.to(self.device, torch.float32).contiguous()
+            prop = self._propagation()
+            perms = _perms
+            B = population_size * num_particles
+            if perms is None:
+                if prop == "fixed_model":
+                    M = len(self.staged.members())
+                    if B % M != 0:
+                        raise ValueError("To use GaussianMLP's ensemble propagation, the batch size must "
+                                         "be a multiple of the number of models in the ensemble.")
+                    if self.ts1 == "perms":
+                        perms = torch.randperm(B, device=self.device).view(1, B)
+                elif prop == "random_model" and self.ts1 == "perms":
+                    perms = torch.stack([torch.randperm(B, device=self.device) for _ in range(horizon)])
+            cfg = _lib.RolloutCfg(population_size, horizon, num_particles, _lib.PREC[self.precision], _lib.PROP[prop],
+                                  _lib.TS1_PERMS if perms is not None else _lib.TS1_TILE_SHUFFLE, self._seed,
+                                  self._next_offset())
+            obs0 = self._obs_to_device(initial_state)
+            returns = torch.empty(population_size, dtype=torch.float32, device=self.device)
+            need = self.lib.b200pets_eval_workspace_bytes(self.staged.handle, C.byref(cfg))
+            ws = self._workspace(need)
+            if perms is not None:
+                perms = perms.to(torch.int64).contiguous()
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.b200pets_eval_sequences(
+                    self.staged.handle, C.byref(cfg), _lib.ptr(obs0), _lib.ptr(actions), _lib.ptr(perms), _lib.ptr(_eps),
+                    _lib.ptr(returns), _lib.ptr(_row_returns), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                    "eval_sequences")
+            return returns
+
+    def _evaluate_stepwise(self, action_sequences, initial_state, num_particles):
+        """evaluate_action_sequences for user callables the kernels do not know: model step on the GPU kernel,
+        reward / termination through the caller's torch functions (model_env.py:170-191 verbatim semantics)."""
+        population_size, horizon, _ = action_sequences.shape
+        tiling = (num_particles * population_size,) + (1,) * initial_state.ndim
+        obs_batch = np.tile(initial_state, tiling).astype(np.float32)
+        keep = self._return_as_np
+        state = self.reset(obs_batch, return_as_np=False)
+        B = obs_batch.shape[0]
+        total = torch.zeros(B, 1, device=self.device)
+        terminated = torch.zeros(B, 1, dtype=torch.bool, device=self.device)
+        for t in range(horizon):
+            a = torch.repeat_interleave(action_sequences[:, t, :].to(self.device), num_particles, dim=0)
+            _, rewards, dones, state = self.step(a, state, sample=True)
+            rewards = rewards.clone()
+            rewards[terminated] = 0
+            terminated |= dones
+            total += rewards
+        self._return_as_np = keep
+        return total.reshape(-1, num_particles).mean(dim=1)

@@ -1,0 +1,122 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/b200pets.h
+declares, configuration plumbing mirrors the reference, and nothing silently falls back to the CPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mbrl_lib_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "b200pets.h")).read()
+    declared = set(re.findall(r"\b(b200pets_[a-z0-9_]+)\s*\(", header))
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in b200pets.h but not exported by libb200pets.so"
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert lib.b200pets_version() == 1
+
+
+def test_no_cpu_fallback_for_models_on_cpu():
+    import mbrl_lib_b200 as bp
+    from mbrl_lib_b200 import functions, synthetic as syn
+
+    spec = syn.CASES["halfcheetah_small"]
+    model = bp.model_from_arrays(spec, syn.make_model_arrays(spec), "cpu")
+
+    class _E:
+        observation_space = None
+        action_space = None
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bp.ModelEnv(_E(), model, functions.no_termination, functions.reward_halfcheetah)
+
+
+def test_callable_resolution():
+    from mbrl_lib_b200 import _lib, functions
+
+    assert functions.resolve_reward(None) == _lib.REWARD["learned"]
+    assert functions.resolve_reward(functions.reward_halfcheetah) == _lib.REWARD["halfcheetah"]
+    assert functions.resolve_term(functions.term_humanoid) == _lib.TERM["humanoid"]
+    assert functions.resolve_reward(lambda a, o: o[:, :1]) == _lib.REWARD["external"]
+
+    def halfcheetah(act, next_obs):  # stands in for mbrl.env.reward_fns.halfcheetah
+        return next_obs[:, :1]
+
+    halfcheetah.__module__ = "mbrl.env.reward_fns"
+    assert functions.resolve_reward(halfcheetah) == _lib.REWARD["halfcheetah"]
+
+    class HalfCheetahEnv:
+        @staticmethod
+        def preprocess_fn(s):
+            return s
+
+    assert functions.resolve_obs_process(HalfCheetahEnv.preprocess_fn) == _lib.PROC["halfcheetah"]
+    with pytest.raises(NotImplementedError):
+        functions.resolve_obs_process(lambda s: s)
+
+
+def test_named_functions_match_oracle():
+    from mbrl_lib_b200 import functions
+    from oracle import pets_oracle as po
+
+    g = torch.Generator().manual_seed(0)
+    obs = torch.randn(64, 20, generator=g)
+    obs[:, 0] = obs[:, 0].abs() + 0.5
+    act = torch.randn(64, 7, generator=g)
+    for name, fn in functions.REWARD_FNS.items():
+        torch.testing.assert_close(fn(act, obs), po.REWARD_FNS[name](act, obs), rtol=1e-5, atol=1e-6)
+    for name, fn in functions.TERM_FNS.items():
+        assert torch.equal(fn(act, obs), po.TERM_FNS[name](act, obs))
+    for name in ("halfcheetah", "cartpole"):
+        torch.testing.assert_close(functions.OBS_PROCESS_FNS[name](obs), po.OBS_PROCESS[name](obs))
+
+
+def test_icem_schedule_matches_reference_rule():
+    import mbrl_lib_b200 as bp
+    from oracle import pets_oracle as po
+
+    lb, ub = [[-1.0] * 3] * 5, [[1.0] * 3] * 5
+    for pop, decay, module in [(1000, 1.3, 7), (48, 1.3, 3), (500, 1.25, None)]:
+        opt = bp.ICEMOptimizer(5, 0.1, pop, decay, 2.0, lb, ub, 0.3, 0.1, "cpu", population_size_module=module)
+        assert opt.population_sizes() == po.icem_population_sizes(5, pop, decay, opt.elite_num, module)
+    opt = bp.ICEMOptimizer(5, 0.1, 1000, 1.3, 2.0, lb, ub, 0.3, 0.1, "cpu", population_size_module=7)
+    assert opt.elite_num == 100 and opt.keep_elite_size == 35
+
+
+def test_target_strings_select_b200_classes():
+    from mbrl_lib_b200 import planning
+
+    cfg = {"_target_": "mbrl.planning.CEMOptimizer", "num_iterations": 2, "elite_ratio": 0.1, "population_size": 10,
+           "alpha": 0.1, "device": "cpu", "return_mean_elites": True}
+    opt = planning._instantiate(cfg, lower_bound=[[-1.0]], upper_bound=[[1.0]])
+    assert isinstance(opt, planning.CEMOptimizer) and opt.elite_num == 1
+    to = planning.TrajectoryOptimizer(cfg, np.array([-1.0, -2.0]), np.array([1.0, 2.0]), planning_horizon=4)
+    assert to.initial_solution.shape == (4, 2) and float(to.initial_solution.abs().max()) == 0.0
+    assert to.optimizer.lower_bound.shape == (4, 2)
+
+
+def test_staging_signature_tracks_training_side_changes():
+    """weights mutate in place, normaliser tensors are replaced, elites change."""
+    import mbrl_lib_b200 as bp
+    from mbrl_lib_b200 import synthetic as syn
+    from mbrl_lib_b200.staging import StagedModel
+
+    spec = syn.CASES["halfcheetah_small"]
+    model = bp.model_from_arrays(spec, syn.make_model_arrays(spec), "cpu")
+    st = StagedModel.__new__(StagedModel)
+    st.src, st.mlp = model, model.model
+    s0 = st._signature()
+    with torch.no_grad():
+        model.model.hidden_layers[1][0].weight.mul_(1.0)
+    s1 = st._signature()
+    model.input_normalizer.mean = model.input_normalizer.mean.clone()
+    s2 = st._signature()
+    model.set_elite([1, 2, 3, 4, 5])
+    s3 = st._signature()
+    assert len({s0, s1, s2, s3}) == 4
