@@ -340,9 +340,17 @@ __global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArg
     s.disp[d] = s.alpha * s.disp[d] + (1.0f - s.alpha) * nd;
   }
   if (s.elites_out) {
-    for (int idx = tid; idx < k * dims; idx += kSelThreads) {
-      const int j = idx / dims, d = idx % dims;
-      s.elites_out[idx] = s.pop[s.elite_idx[j] * s.pstride + d];
+    // the reference keeps `population[elite_idx]` in topk order (descending value, trajectory_opt.py:475-476) and
+    // iCEM indexes that order with randperm: emit rows by descending value (ties: lower population index first)
+    for (int e = tid; e < k; e += kSelThreads) {
+      const int ie = s.elite_idx[e];
+      const float ve = s.values[ie * s.vstride];
+      int rank = 0;
+      for (int f = 0; f < k; ++f) {
+        const float vf = s.values[s.elite_idx[f] * s.vstride];
+        rank += (vf > ve || (vf == ve && f < e)) ? 1 : 0;
+      }
+      for (int d = 0; d < dims; ++d) s.elites_out[(size_t)rank * dims + d] = s.pop[ie * s.pstride + d];
     }
   }
   // ---- best-so-far (trajectory_opt.py:184-186) ----

@@ -82,6 +82,8 @@ class CEMOptimizer(Optimizer):
         self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self._ws = None
         self._plan_ws = None
+        self.record_values = False
+        self.last_values = None
 
     def _buffers(self, shape):
         dims = int(np.prod(shape))
@@ -160,13 +162,14 @@ class CEMOptimizer(Optimizer):
         z = None if noise is None else noise.to(self.device, torch.float32).contiguous()
         if perms is not None:
             perms = perms.to(torch.int64).contiguous()
-        self._last_values = getattr(self, "_want_values", False) and torch.empty(
-            self.num_iterations, self.population_size, device=self.device) or None
+        self.last_values = None
+        if self.record_values:  # per-iteration objective values of the fused plan (diagnostics / tests)
+            self.last_values = torch.empty(self.num_iterations, self.population_size, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.b200pets_cem_plan(
                 env.staged.handle, C.byref(rcfg), C.byref(ccfg), _lib.ptr(obs0), _lib.ptr(x0), _lib.ptr(self.lower_bound),
                 _lib.ptr(self.upper_bound), _lib.ptr(z), _lib.ptr(eps), _lib.ptr(perms), _lib.ptr(sol),
-                _lib.ptr(self._last_values), _lib.ptr(self._plan_ws), self._plan_ws.numel(), _lib.stream_ptr()), "cem_plan")
+                _lib.ptr(self.last_values), _lib.ptr(self._plan_ws), self._plan_ws.numel(), _lib.stream_ptr()), "cem_plan")
         return sol.view(H, A)
 
 
