@@ -6,9 +6,10 @@
 // epilogue warps straight into the UMMA canonical shared-memory layout and whose B operand (weights) is
 // streamed from the L2-resident packed image through a ring of 1-D TMA bulk copies.
 //
-// Warp roles (192 threads):  warp 0 = weight producer (cp.async.bulk + mbarrier),
+// Warp roles (64 + 128 * CS threads):  warp 0 = weight producer (cp.async.bulk + mbarrier),
 //                            warp 1 = TMEM allocator + MMA issuer (single thread),
-//                            warps 2..5 = epilogue: thread i <-> tile row i <-> TMEM lane i.
+//                            warps 2.. = 4 * CS epilogue warps: warp (q, cs) <-> TMEM lanes 32q..32q+31 (tile rows)
+//                            and every CS-th 16-column chunk; thread (row, cs == 0) owns the row's scalar state.
 //
 // Bias is folded into the GEMM: every A tile carries two constant-one columns after the real inputs and the
 // packed weight image carries bf16(b) and bf16(b - bf16(b)) in the matching K rows (api.cu pack kernel).
@@ -32,7 +33,7 @@ struct TcPlan {
 
 namespace {
 
-constexpr int kTcThreads = 192;
+constexpr int kEpiSplit = 4;  // column splits of the epilogue (16 epilogue warps)
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 
@@ -55,9 +56,13 @@ __device__ __forceinline__ float act_tc(float x, float slope) {
 // byte offset of the 16-byte chunk (row i, k-chunk kc) in the A tile: [kc][i / 8][i % 8][8 x bf16]
 __device__ __forceinline__ uint32_t a_chunk_off(int i, int kc) { return (uint32_t)((kc * 16 + (i >> 3)) * 128 + (i & 7) * 16); }
 
-template <int ACT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// CS = column splits of the epilogue: 4 * CS epilogue warps; warp (q, cs) owns TMEM lane quadrant q (rows
+// 32q..32q+31) and every CS-th 16-column chunk.  Thread (row i, cs == 0) also owns the row's scalar state.
+template <int ACT, int CS>
+__global__ void __launch_bounds__(64 + 128 * CS, 1)
 rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const long long num_tiles) {
+  constexpr int kEpiThreads = 128 * CS;
+  constexpr int kThreadsAll = 64 + kEpiThreads;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* A_s = smem + p.off_A;
   uint8_t* ring = smem + p.off_ring;
@@ -68,6 +73,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
   float* c_minlv = c_istd + m.in;
   float* c_maxlv = c_minlv + m.out;
   float* c_nodelta = c_maxlv + m.out;  // [D] 1.0 = keep raw prediction
+  float* rew_s = c_nodelta + m.D;      // [128] learned-reward column of the current step
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* bar_empty = bar_full + kMaxStages;
   uint64_t* bar_a_ready = bar_empty + kMaxStages;
@@ -82,19 +88,19 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    mbar_init(bar_a_ready, kTileM);
+    mbar_init(bar_a_ready, kEpiThreads);
     mbar_init(bar_acc, 1);
     mbar_fence_init();
   }
-  for (int j = threadIdx.x; j < m.in; j += kTcThreads) {
+  for (int j = threadIdx.x; j < m.in; j += kThreadsAll) {
     c_mean[j] = m.norm_mode ? m.norm_mean_f[j] : 0.f;
     c_istd[j] = m.norm_mode ? m.norm_istd_f[j] : 1.f;
   }
-  for (int j = threadIdx.x; j < m.out; j += kTcThreads) {
+  for (int j = threadIdx.x; j < m.out; j += kThreadsAll) {
     c_minlv[j] = m.deterministic ? 0.f : m.min_lv[j];
     c_maxlv[j] = m.deterministic ? 0.f : m.max_lv[j];
   }
-  for (int j = threadIdx.x; j < m.D; j += kTcThreads) c_nodelta[j] = (!m.target_is_delta || m.no_delta[j]) ? 1.f : 0.f;
+  for (int j = threadIdx.x; j < m.D; j += kThreadsAll) c_nodelta[j] = (!m.target_is_delta || m.no_delta[j]) ? 1.f : 0.f;
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -168,14 +174,18 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     }
     __syncwarp();
   } else {
-    // =========================== epilogue: thread i <-> row i ===========================
-    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    // =========================== epilogue ===========================
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access (hardware: warp id % 4)
+    const int cs = (warp - 2) >> 2;    // column split
     const int i = q * 32 + lane;       // tile row
+    const bool owner = cs == 0;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* my_obs = obs_s + i * p.obs_ld;
     float* my_act = act_s + i * p.act_ld;
     uint32_t acc_par = 0;
     const int Kp0 = m.Kp[0];
+    const int ngroups = (m.out + 3) >> 2;
+    auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
 
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       long long slot0;
@@ -191,27 +201,30 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
       }
       const bool valid = i < nv;
       const long long rid = valid ? slot_to_rid(a, slot0 + i) : 0;
-      // ---- load row state ----
-      for (int d = 0; d < m.D; ++d) {
-        float v = 0.f;
-        if (valid) v = a.init_from_obs0 ? a.obs0[d] : a.obs_in[rid * m.D + d];
-        my_obs[d] = v;
-      }
       float tot = 0.f;
       int dead = 0;
-      if (a.load_state && valid) {
-        tot = a.total_state[rid];
-        dead = a.dead_state[rid];
+      epi_bar();  // previous tile fully consumed before its row state is overwritten
+      if (owner) {
+        for (int d = 0; d < m.D; ++d) {
+          float v = 0.f;
+          if (valid) v = a.init_from_obs0 ? a.obs0[d] : a.obs_in[rid * m.D + d];
+          my_obs[d] = v;
+        }
+        if (a.load_state && valid) {
+          tot = a.total_state[rid];
+          dead = a.dead_state[rid];
+        }
       }
+      const float* act_row = a.act + (rid / a.act_div) * a.act_row_stride;
 
       for (int t = a.t0; t < a.t1; ++t) {
-        // ---- actions of this step ----
-        {
-          const float* ap = a.act + (rid / a.act_div) * a.act_row_stride + (long long)t * a.act_t_stride;
+        if (owner) {
+          const float* ap = act_row + (long long)t * a.act_t_stride;
           for (int j = 0; j < m.A; ++j) my_act[j] = valid ? ap[j] : 0.f;
         }
+        epi_bar();
         // ---- layer-0 operand: normalise(cat(proc(obs), act)), two constant-one bias columns, zero pad ----
-        for (int kc = 0; kc < Kp0 / 8; ++kc) {
+        for (int kc = cs; kc < Kp0 / 8; kc += CS) {
           float x[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -241,7 +254,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           mbar_wait(bar_acc, acc_par);
           acc_par ^= 1u;
           tc_fence_after();
-          for (int c = 0; c < kp_next / 16; ++c) {
+          for (int c = cs; c < kp_next / 16; c += CS) {
             float v[16];
             if (16 * c < np) {
               uint32_t r[16];
@@ -270,24 +283,26 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           mbar_arrive(bar_a_ready);
         }
 
-        // ---- output layer: Gaussian sample, delta add-back, reward, termination ----
+        // ---- output layer: groups of 4 outputs; Gaussian sample, delta add-back ----
         mbar_wait(bar_acc, acc_par);
         acc_par ^= 1u;
         tc_fence_after();
-        float rew_pred = 0.f;
-        for (int qc = 0; qc < m.outp / 16; ++qc) {
-          uint32_t rm[16], rl[16];
-          tmem_ld16(t_lane + (uint32_t)(16 * qc), rm);
-          if (!m.deterministic) tmem_ld16(t_lane + (uint32_t)(m.outp + 16 * qc), rl);
+        for (int g = cs; g < ngroups; g += CS) {
+          uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
+          tmem_ld4(t_lane + (uint32_t)(4 * g), rm);
+          if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * g), rl);
           tmem_ld_wait();
           float z[4] = {0.f, 0.f, 0.f, 0.f};
+          const bool draw = !m.deterministic && a.sample;
+          if (draw && !a.eps)
+            philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)g, (uint32_t)a.offset, a.seed, z);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int o = 16 * qc + e;
+          for (int e = 0; e < 4; ++e) {
+            const int o = 4 * g + e;
             if (o < m.out) {
               const float mean = __uint_as_float(rm[e]);
               float pred = mean;
-              if (!m.deterministic && a.sample) {
+              if (draw) {
                 float lv = __uint_as_float(rl[e]);
                 const float mx = c_maxlv[o], mn = c_minlv[o];
                 float d1 = mx - lv;
@@ -295,18 +310,11 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
                 float d2 = lv - mn;
                 lv = mn + (d2 > 20.f ? d2 : __logf(1.f + __expf(d2)));
                 const float sd = __expf(0.5f * lv);
-                float ev;
-                if (a.eps) {
-                  ev = valid ? a.eps[((size_t)(t - a.t0) * a.B + rid) * m.out + o] : 0.f;
-                } else {
-                  if ((e & 3) == 0)
-                    philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)(o >> 2), (uint32_t)a.offset, a.seed, z);
-                  ev = z[e & 3];
-                }
+                const float ev = a.eps ? (valid ? a.eps[((size_t)(t - a.t0) * a.B + rid) * m.out + o] : 0.f) : z[e];
                 pred = fmaf(sd, ev, mean);
               }
               if (m.learned_rewards && o == m.out - 1) {
-                rew_pred = pred;
+                rew_s[i] = pred;
               } else {
                 my_obs[o] = c_nodelta[o] != 0.f ? pred : pred + my_obs[o];
               }
@@ -314,8 +322,10 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           }
         }
         tc_fence_before();
-        {
-          float rew = m.learned_rewards ? rew_pred : reward_eval(m.reward_fn, my_act, m.A, 1, my_obs, m.D, 1);
+        epi_bar();
+        // ---- reward, termination, accumulate: the row's owner thread ----
+        if (owner) {
+          float rew = m.learned_rewards ? rew_s[i] : reward_eval(m.reward_fn, my_act, m.A, 1, my_obs, m.D, 1);
           const bool done = term_eval(m.term_fn, my_obs, m.D, 1);
           if (valid) {
             if (a.reward_out) a.reward_out[rid] = rew;
@@ -327,7 +337,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         }
       }
       // ---- store row state ----
-      if (a.store_state && valid) {
+      if (owner && a.store_state && valid) {
         if (a.obs_out)
           for (int d = 0; d < m.D; ++d) a.obs_out[rid * m.D + d] = my_obs[d];
         if (a.total_state) a.total_state[rid] = tot;
@@ -441,7 +451,7 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   p.off_A = off; off += (uint32_t)kTileM * kp_max * 2;
   p.off_obs = off; off += (uint32_t)kTileM * p.obs_ld * 4;
   p.off_act = off; off += (uint32_t)kTileM * p.act_ld * 4;
-  p.off_const = off; off += (uint32_t)(2 * m.in + 2 * m.out + m.D) * 4;
+  p.off_const = off; off += (uint32_t)(2 * m.in + 2 * m.out + m.D + kTileM) * 4;
   off = (off + 15u) & ~15u;
   p.off_bar = off; off += (2 * kMaxStages + 2) * 8 + 16;
   off = (off + 127u) & ~127u;
@@ -479,12 +489,12 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
   const unsigned grid = (unsigned)min((long long)g_sm_count, tiles);
   void (*kern)(const ModelDev, const RolloutArgs, const TcPlan, const long long) = nullptr;
   switch (m.act) {
-    case B200PETS_ACT_SILU: kern = rollout_tc_kernel<B200PETS_ACT_SILU>; break;
-    case B200PETS_ACT_RELU: kern = rollout_tc_kernel<B200PETS_ACT_RELU>; break;
-    default: kern = rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU>; break;
+    case B200PETS_ACT_SILU: kern = rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit>; break;
+    case B200PETS_ACT_RELU: kern = rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit>; break;
+    default: kern = rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit>; break;
   }
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-  kern<<<grid, kTcThreads, p.smem_bytes, stream>>>(m, a, p, tiles);
+  kern<<<grid, 64 + 128 * kEpiSplit, p.smem_bytes, stream>>>(m, a, p, tiles);
   CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }
