@@ -222,9 +222,19 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
                       const float* z, const float* eps, const int64_t* perms, float* solution,
                       float* values_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostics: when stamps [dev] int64[128] is non-NULL, CTA 0 of every tensor-core rollout launch writes clock64()
+ * stamps of one horizon step (epilogue thread: slots 0.., MMA thread: slots 64 + 4 * layer ..); NULL disables. */
+int b200pets_debug_timeline(int64_t* stamps);
+
+/* Diagnostics: cycles [dev] int64[2] <- (issue, issue+complete) clock64 cycles of reps x (k/16) back-to-back
+ * tcgen05.mma M=128 x n with operand layout `mode` (0 = the rollout kernel's no-swizzle layout, 1 = SWIZZLE_128B,
+ * 2 = no-swizzle with adjacent K halves).  Timing only. */
+int b200pets_debug_umma_bench(int32_t mode, int32_t k, int32_t n, int32_t reps, int64_t* cycles, void* stream);
+
 /* Self test of the tcgen05 building block: D[128][n] = A[128][k] * B[n][k]^T with bf16 operands staged in
  * the no-swizzle canonical layout the rollout kernel uses.  a, b [dev] float (rounded to bf16 inside),
- * d [dev] float[128][n].  k, n multiples of 16, n <= 256. */
+ * d [dev] float[128][n].  k, n multiples of 16, n <= 256.  A negative k runs the A-from-TMEM (tcgen05.st -> .ts MMA)
+ * form with |k|. */
 int b200pets_selftest_umma(int32_t k, int32_t n, const float* a, const float* b, float* d, void* stream);
 
 #ifdef __cplusplus

@@ -71,6 +71,8 @@ _SIGNATURES = {
     "b200pets_cem_plan_workspace_bytes": (C.c_size_t, [_P, C.POINTER(RolloutCfg), C.POINTER(CemCfg)]),
     "b200pets_cem_plan": (C.c_int, [_P, C.POINTER(RolloutCfg), C.POINTER(CemCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                     C.c_size_t, _P]),
+    "b200pets_debug_timeline": (C.c_int, [_P]),
+    "b200pets_debug_umma_bench": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "b200pets_selftest_umma": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P]),
 }
 

@@ -15,6 +15,7 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
 int launch_umma_selftest(int k, int n, const float* a, const float* b, float* d, cudaStream_t stream);
 int launch_particle_mean(int N, int P, const float* total, float* returns, cudaStream_t stream);
 bool tc_supported(const ModelDev& m);
+int launch_umma_bench(int mode, int k, int n, int reps, long long* out, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------
 // errors
@@ -142,6 +143,10 @@ static int stage_model(b200pets_model_s* mdl, const float* const* weights, const
           v.Np[l], d.out_size, v.outp, l == layers - 1, d.deterministic);
     }
   }
+  if (mdl->tc_ok)
+    for (int r = 1; r < v.img_replicas; ++r)
+      CUDA_TRY(cudaMemcpyAsync(mdl->blob + mdl->off_img + (size_t)r * v.img_replica_stride, mdl->blob + mdl->off_img,
+                               (size_t)v.img_member_stride * d.num_members, cudaMemcpyDeviceToDevice, stream));
   CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }
@@ -210,7 +215,9 @@ int b200pets_model_create(const b200pets_model_desc* desc, const float* const* w
   mdl->off_norm_f = take(sizeof(float) * 3 * d.in_size);
   mdl->off_lv = take(sizeof(float) * 2 * d.out_size);
   mdl->off_nodelta = take(d.obs_dim);
-  mdl->off_img = take((size_t)v.img_member_stride * d.num_members);
+  v.img_replicas = 8;
+  v.img_replica_stride = ((v.img_member_stride * (uint32_t)d.num_members) + 255u) & ~255u;
+  mdl->off_img = take((size_t)v.img_replica_stride * v.img_replicas);
   mdl->blob_bytes = off;
   cudaError_t e = cudaMalloc(&mdl->blob, mdl->blob_bytes);
   if (e != cudaSuccess) {
@@ -263,7 +270,11 @@ int b200pets_model_supports_tc(b200pets_model_t model) { return model && model->
 // ---------------------------------------------------------------------------------------------------------
 // rollouts
 // ---------------------------------------------------------------------------------------------------------
-static int dispatch(const b200pets_model_s* mdl, int precision, const RolloutArgs& a, cudaStream_t stream) {
+static long long* g_timeline = nullptr;
+
+static int dispatch(const b200pets_model_s* mdl, int precision, const RolloutArgs& a_in, cudaStream_t stream) {
+  RolloutArgs a = a_in;
+  a.timeline = g_timeline;
   if (precision == B200PETS_PREC_BF16_TC) {
     if (!mdl->tc_ok) return b200pets_set_error(B200PETS_EUNSUPPORTED, "tensor-core path does not cover this model; use B200PETS_PREC_F32");
     return launch_rollout_tc(mdl->dev, a, stream);
@@ -441,6 +452,15 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
   }
   CUDA_TRY(cudaMemcpyAsync(solution, ccfg->return_mean_elites ? mu : best_sol, sizeof(float) * dims, cudaMemcpyDeviceToDevice, stream));
   return B200PETS_OK;
+}
+
+int b200pets_debug_timeline(int64_t* stamps) {
+  g_timeline = reinterpret_cast<long long*>(stamps);
+  return B200PETS_OK;
+}
+
+int b200pets_debug_umma_bench(int32_t mode, int32_t k, int32_t n, int32_t reps, int64_t* cycles, void* stream) {
+  return launch_umma_bench(mode, k, n, reps, reinterpret_cast<long long*>(cycles), (cudaStream_t)stream);
 }
 
 int b200pets_selftest_umma(int32_t k, int32_t n, const float* a, const float* b, float* d, void* stream) {

@@ -28,6 +28,8 @@ struct ModelDev {
   // tensor-core images (bf16, UMMA no-swizzle K-major canonical layout), see rollout_tc.cu
   const uint8_t* img;                   // base of member 0
   uint32_t img_member_stride;           // bytes between members
+  uint32_t img_replica_stride;          // bytes between replicas of the whole image set
+  int img_replicas;                     // copies at distinct addresses: spreads simultaneous readers over L2 slices
   uint32_t img_layer_off[B200PETS_MAX_LAYERS];
   int Kp[B200PETS_MAX_LAYERS], Np[B200PETS_MAX_LAYERS];
   int outp;                             // padded out (multiple of 16): logvar columns start here
@@ -61,6 +63,7 @@ struct RolloutArgs {
   // step outputs (b200pets_step): next_obs = obs_out, reward, done
   float* reward_out;       // [B] or NULL
   uint8_t* done_out;       // [B] or NULL
+  long long* timeline;     // diagnostics: clock64 stamps of CTA 0 (b200pets_debug_timeline) or NULL
 };
 
 // ------------------------------------------------------------------------------------------------------

@@ -121,15 +121,25 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         const int member = shuffle ? 0 : (int)(tile / tpm);
         for (int t = a.t0; t < a.t1; ++t) {
           const int mem = shuffle ? shuffle_member(a, (int)tile, t, m.M) : member;
-          const uint8_t* base = m.img + (size_t)mem * m.img_member_stride;
+          const uint8_t* base = m.img + (size_t)(blockIdx.x % m.img_replicas) * m.img_replica_stride + (size_t)mem * m.img_member_stride;
           for (int l = 0; l < nlayers; ++l) {
             const uint8_t* lsrc = base + m.img_layer_off[l];
+            const uint32_t col_bytes = (uint32_t)m.Np[l] * 16u;  // one K core column (8 K-rows x Np)
             for (int j = 0; j < p.nblk[l]; ++j) {
               const int kb = min(64, m.Kp[l] - 64 * j);
-              const uint32_t bytes = (uint32_t)kb * m.Np[l] * 2u;
+              const int ncol = kb >> 3;
+              const uint32_t bytes = (uint32_t)ncol * col_bytes;
               mbar_wait(&bar_empty[stage], phase ^ 1u);
               mbar_arrive_expect_tx(&bar_full[stage], bytes);
-              bulk_g2s(ring + (size_t)stage * p.stage_bytes, lsrc + (size_t)64 * j * m.Np[l] * 2, bytes, &bar_full[stage]);
+              uint8_t* dst = ring + (size_t)stage * p.stage_bytes;
+              const uint8_t* src = lsrc + (size_t)64 * j * m.Np[l] * 2;
+              // the columns of a stage may land in any order: start at a CTA-dependent column so that CTAs streaming
+              // the same member do not walk the same L2 lines in lockstep
+              int c = (int)((blockIdx.x >> 3) % ncol);
+              for (int q = 0; q < ncol; ++q) {
+                bulk_g2s(dst + (size_t)c * col_bytes, src + (size_t)c * col_bytes, col_bytes, &bar_full[stage]);
+                if (++c == ncol) c = 0;
+              }
               if (++stage == S) { stage = 0; phase ^= 1u; }
             }
           }
@@ -150,13 +160,17 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
             const uint32_t np = (uint32_t)m.Np[l];
             const uint32_t idesc = umma_idesc_bf16_m128(np);
             const uint32_t b_lbo = np * 16u;
+            const bool stamp = a.timeline && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x;
+            if (stamp) a.timeline[64 + l * 4 + 0] = clock64();
             mbar_wait(bar_a_ready, a_par);
             a_par ^= 1u;
             tc_fence_after();
+            if (stamp) a.timeline[64 + l * 4 + 1] = clock64();
             for (int j = 0; j < p.nblk[l]; ++j) {
               const int kb = min(64, m.Kp[l] - 64 * j);
               mbar_wait(&bar_full[stage], phase);
               tc_fence_after();
+              if (stamp && j == p.nblk[l] - 1) a.timeline[64 + l * 4 + 2] = clock64();
               const uint32_t b_addr = ring_addr + (uint32_t)stage * p.stage_bytes;
               for (int kk = 0; kk < kb / 16; ++kk) {
                 const uint32_t k0 = (uint32_t)(64 * j + 16 * kk);
@@ -168,6 +182,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
               if (++stage == S) { stage = 0; phase ^= 1u; }
             }
             umma_commit(bar_acc);
+            if (stamp) a.timeline[64 + l * 4 + 3] = clock64();
           }
         }
       }
@@ -216,13 +231,30 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         }
       }
       const float* act_row = a.act + (rid / a.act_div) * a.act_row_stride;
+      const bool act_regs = m.A <= 8;  // next-step actions prefetched into registers (hidden behind the layers)
+      float an[8];
+      if (owner) {
+        const float* ap = act_row + (long long)a.t0 * a.act_t_stride;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) an[j] = (valid && j < m.A) ? ap[j] : 0.f;
+      }
 
       for (int t = a.t0; t < a.t1; ++t) {
+        const bool stamp = a.timeline && blockIdx.x == 0 && warp == 2 && lane == 0 && t == a.t0 + 5 && tile == blockIdx.x;
+        int sp = 0;
+        if (stamp) a.timeline[sp++] = clock64();  // 0: step start
         if (owner) {
-          const float* ap = act_row + (long long)t * a.act_t_stride;
-          for (int j = 0; j < m.A; ++j) my_act[j] = valid ? ap[j] : 0.f;
+          if (act_regs) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < m.A) my_act[j] = an[j];
+          } else {
+            const float* ap = act_row + (long long)t * a.act_t_stride;
+            for (int j = 0; j < m.A; ++j) my_act[j] = valid ? ap[j] : 0.f;
+          }
         }
         epi_bar();
+        if (stamp) a.timeline[sp++] = clock64();  // 1: actions loaded + barrier
         // ---- layer-0 operand: normalise(cat(proc(obs), act)), two constant-one bias columns, zero pad ----
         for (int kc = cs; kc < Kp0 / 8; kc += CS) {
           float x[8];
@@ -245,6 +277,21 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_a_ready);
+        if (stamp) a.timeline[sp++] = clock64();  // 2: input built
+        // work hidden behind the first MMAs: next step's actions (global loads) and this step's model noise
+        if (owner && act_regs && t + 1 < a.t1) {
+          const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) an[j] = (valid && j < m.A) ? ap[j] : 0.f;
+        }
+        const bool draw = !m.deterministic && a.sample;
+        float zpre[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int g = cs + u * CS;
+          if (draw && !a.eps && g < ngroups)
+            philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)g, (uint32_t)a.offset, a.seed, zpre[u]);
+        }
 
         // ---- hidden layers: TMEM accumulator -> activation -> bf16 -> next A operand ----
         for (int l = 0; l < nlayers - 1; ++l) {
@@ -254,6 +301,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           mbar_wait(bar_acc, acc_par);
           acc_par ^= 1u;
           tc_fence_after();
+          if (stamp) a.timeline[sp++] = clock64();  // 3 + 2l: accumulator ready
           for (int c = cs; c < kp_next / 16; c += CS) {
             float v[16];
             if (16 * c < np) {
@@ -281,21 +329,29 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           tc_fence_before();
           fence_proxy_async_smem();
           mbar_arrive(bar_a_ready);
+          if (stamp) a.timeline[sp++] = clock64();  // 4 + 2l: activations written
         }
 
         // ---- output layer: groups of 4 outputs; Gaussian sample, delta add-back ----
         mbar_wait(bar_acc, acc_par);
         acc_par ^= 1u;
         tc_fence_after();
+        if (stamp) a.timeline[sp++] = clock64();  // output accumulator ready
         for (int g = cs; g < ngroups; g += CS) {
           uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
           tmem_ld4(t_lane + (uint32_t)(4 * g), rm);
           if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * g), rl);
           tmem_ld_wait();
           float z[4] = {0.f, 0.f, 0.f, 0.f};
-          const bool draw = !m.deterministic && a.sample;
-          if (draw && !a.eps)
-            philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)g, (uint32_t)a.offset, a.seed, z);
+          if (draw && !a.eps) {
+            const int u = (g - cs) / CS;
+            if (u < 2) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) z[e] = u == 0 ? zpre[0][e] : zpre[1][e];
+            } else {
+              philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)g, (uint32_t)a.offset, a.seed, z);
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int o = 4 * g + e;
@@ -322,7 +378,9 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           }
         }
         tc_fence_before();
+        if (stamp) a.timeline[sp++] = clock64();  // outputs sampled
         epi_bar();
+        if (stamp) a.timeline[sp++] = clock64();  // barrier
         // ---- reward, termination, accumulate: the row's owner thread ----
         if (owner) {
           float rew = m.learned_rewards ? rew_s[i] : reward_eval(m.reward_fn, my_act, m.A, 1, my_obs, m.D, 1);
@@ -335,6 +393,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           dead |= done ? 1 : 0;
           tot += rew;
         }
+        if (stamp) a.timeline[sp++] = clock64();  // reward done
       }
       // ---- store row state ----
       if (owner && a.store_state && valid) {
@@ -408,6 +467,147 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int k, int n, con
     tmem_ld_wait();
     for (int e = 0; e < 16; ++e) D[i * n + 16 * c + e] = __uint_as_float(r[e]);
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+
+// self test of the A-from-TMEM form: the four warps write their rows of A (bf16 pairs) with tcgen05.st
+__global__ void __launch_bounds__(128, 1) umma_selftest_ts_kernel(int k, int n, const float* __restrict__ A,
+                                                                   const float* __restrict__ B, float* __restrict__ D) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* B_s = smem;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(B_s + n * k * 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  for (int idx = tid; idx < n * (k / 8); idx += 128) {
+    int nn = idx % n, kc = idx / n;
+    float x[8];
+    for (int e = 0; e < 8; ++e) x[e] = B[nn * k + kc * 8 + e];
+    *reinterpret_cast<uint4*>(B_s + (size_t)(kc * (n / 8) + (nn >> 3)) * 128 + (nn & 7) * 16) =
+        make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+  }
+  fence_proxy_async_smem();
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t a_col = 256;
+  const int i = warp * 32 + lane;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int kk = 0; kk < k / 16; ++kk) {
+    uint32_t r[8];
+    for (int e = 0; e < 8; ++e) r[e] = pack_bf16(A[i * k + kk * 16 + 2 * e], A[i * k + kk * 16 + 2 * e + 1]);
+    tmem_st8(t_lane + a_col + (uint32_t)(8 * kk), r);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)n);
+    const uint32_t b_lbo = (uint32_t)n * 16u;
+    for (int kk = 0; kk < k / 16; ++kk) {
+      const uint64_t bdesc = umma_smem_desc(smem_u32(B_s) + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128u);
+      umma_bf16_ts(tmem_base, tmem_base + a_col + (uint32_t)(8 * kk), bdesc, idesc, kk != 0 ? 1u : 0u);
+    }
+    umma_commit(bar);
+  }
+  __syncwarp();
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  for (int c = 0; c < n / 16; ++c) {
+    uint32_t r[16];
+    tmem_ld16(t_lane + (uint32_t)(16 * c), r);
+    tmem_ld_wait();
+    for (int e = 0; e < 16; ++e) D[i * n + 16 * c + e] = __uint_as_float(r[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// micro-benchmark: issue rate of back-to-back tcgen05.mma for different shared-memory operand layouts
+//   mode 0: no swizzle, K core columns strided (LBO = rows*16, SBO = 128)      <- layout of the rollout kernel
+//   mode 1: SWIZZLE_128B K-major (SBO = 1024, 32 B start-address advance per K step inside a 64-element block)
+//   mode 2: no swizzle, the two K halves of a row group adjacent (LBO = 128, SBO = (K/8)*128)
+// Data is whatever is in shared memory: timing only.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;                      // LBO (unused for swizzled K-major)
+  d |= (uint64_t)((1024u >> 4) & 0x3FFFu) << 32;  // SBO: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int k, int n, int reps, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* A_s = smem;
+  uint8_t* B_s = smem + 128 * 256 * 2;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + 256) * 256 * 2 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)n);
+    const uint32_t a0 = smem_u32(A_s), b0 = smem_u32(B_s);
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int kk = 0; kk < (mode == 3 ? 0 : k / 16); ++kk) {
+        uint64_t ad, bd;
+        if (mode == 0) {
+          ad = umma_smem_desc(a0 + (uint32_t)(2 * kk) * 2048u, 2048u, 128u);
+          bd = umma_smem_desc(b0 + (uint32_t)(2 * kk) * (uint32_t)n * 16u, (uint32_t)n * 16u, 128u);
+        } else if (mode == 1) {
+          ad = umma_smem_desc_sw128(a0 + (uint32_t)(kk >> 2) * 128u * 128u + (uint32_t)(kk & 3) * 32u);
+          bd = umma_smem_desc_sw128(b0 + (uint32_t)(kk >> 2) * (uint32_t)n * 128u + (uint32_t)(kk & 3) * 32u);
+        } else {
+          ad = umma_smem_desc(a0 + (uint32_t)kk * 256u, 128u, (uint32_t)(k / 8) * 128u);
+          bd = umma_smem_desc(b0 + (uint32_t)kk * 256u, 128u, (uint32_t)(k / 8) * 128u);
+        }
+        if (mode != 3) umma_bf16_ss(tmem_base, ad, bd, idesc, 1u);
+      }
+      if (mode == 3) {  // tight issue: precomputed descriptors, start-address field advanced by a constant
+        uint64_t ad = umma_smem_desc(a0, 2048u, 128u), bd = umma_smem_desc(b0, (uint32_t)n * 16u, 128u);
+        const uint64_t a_inc = (2u * 2048u) >> 4, b_inc = (2u * (uint32_t)n * 16u) >> 4;
+        const int nk = k / 16;
+#pragma unroll 4
+        for (int kk = 0; kk < nk; ++kk) {
+          umma_bf16_ss(tmem_base, ad, bd, idesc, 1u);
+          ad += a_inc;
+          bd += b_inc;
+        }
+      }
+    }
+    long long t1 = clock64();
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  __syncthreads();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -500,11 +700,29 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
 }
 
 int launch_umma_selftest(int k, int n, const float* a, const float* b, float* d, cudaStream_t stream) {
+  const bool ts = k < 0;  // negative k selects the A-from-TMEM form
+  if (ts) k = -k;
   if (k % 16 || n % 16 || n > 256 || k > 256 || k < 16 || n < 16)
     return b200pets_set_error(B200PETS_EINVAL, "selftest needs k, n multiples of 16, <= 256");
+  if (ts) {
+    size_t smem_ts = (size_t)n * k * 2 + 64;
+    CUDA_TRY(cudaFuncSetAttribute(umma_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
+    umma_selftest_ts_kernel<<<1, 128, smem_ts, stream>>>(k, n, a, b, d);
+    CUDA_TRY(cudaGetLastError());
+    return B200PETS_OK;
+  }
   size_t smem = (size_t)128 * k * 2 + (size_t)n * k * 2 + 64;
   CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_selftest_kernel<<<1, 128, smem, stream>>>(k, n, a, b, d);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}
+
+int launch_umma_bench(int mode, int k, int n, int reps, long long* out, cudaStream_t stream) {
+  if (k % 16 || n % 16 || n > 256 || k > 256) return b200pets_set_error(B200PETS_EINVAL, "umma_bench: bad shape");
+  size_t smem = (size_t)(128 + 256) * 256 * 2 + 1024;
+  CUDA_TRY(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_bench_kernel<<<1, 128, smem, stream>>>(mode, k, n, reps, out);
   CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }

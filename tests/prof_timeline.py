@@ -1,0 +1,24 @@
+"""Diagnostics: per-phase clock64 stamps of one horizon step of CTA 0 (tensor-core rollout)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from mbrl_lib_b200 import synthetic as syn, _lib
+
+spec, arrays, env = bench.build_problem("cuda:0")
+inp = syn.make_rollout_inputs(spec, with_noise=False)
+acts = torch.from_numpy(inp["actions"]).to("cuda:0")
+lib = _lib.load()
+buf = torch.zeros(128, dtype=torch.int64, device="cuda:0")
+for _ in range(3):
+    env.evaluate_action_sequences(acts, inp["obs0"], spec.particles)
+lib.b200pets_debug_timeline(_lib.ptr(buf))
+env.evaluate_action_sequences(acts, inp["obs0"], spec.particles)
+torch.cuda.synchronize()
+lib.b200pets_debug_timeline(None)
+b = buf.cpu().tolist()
+t0 = b[0]
+print("epilogue thread stamps (cycles since step start):", [x - t0 for x in b[:20] if x])
+for l in range(5):
+    s = b[64 + 4 * l: 68 + 4 * l]
+    print(f"mma layer {l}: wait_a_start {s[0]-t0}, a_ready {s[1]-t0}, last_stage_full {s[2]-t0}, issued {s[3]-t0}")

@@ -92,15 +92,17 @@ def test_library_on_b200():
     assert ma.value == 10, f"built for sm_100a, running on sm_{ma.value}{mi.value}"
 
 
-@pytest.mark.parametrize("k,n", [(16, 16), (32, 208), (208, 208), (208, 64), (256, 256), (64, 48)])
+@pytest.mark.parametrize("k,n", [(16, 16), (32, 208), (208, 208), (208, 64), (256, 256), (64, 48),
+                                 (-16, 16), (-32, 208), (-208, 208), (-208, 64), (-256, 256), (-208, 112)])
 def test_umma_selftest(k, n):
     """tcgen05.mma through the no-swizzle canonical layouts / descriptors used by the rollout kernel."""
     from mbrl_lib_b200 import _lib
 
     lib = _lib.load()
-    g = torch.Generator().manual_seed(k * 1000 + n)
-    a = torch.randn(128, k, generator=g)
-    b = torch.randn(n, k, generator=g)
+    ka = abs(k)  # negative k: A operand from TMEM
+    g = torch.Generator().manual_seed(ka * 1000 + n)
+    a = torch.randn(128, ka, generator=g)
+    b = torch.randn(n, ka, generator=g)
     ad, bd = a.to(DEV), b.to(DEV)
     d = torch.zeros(128, n, device=DEV)
     _lib.check(lib.b200pets_selftest_umma(k, n, _lib.ptr(ad), _lib.ptr(bd), _lib.ptr(d), _lib.stream_ptr()))
