@@ -91,8 +91,8 @@ __device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0, 1)
   return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
 }
 
-// four N(0,1) draws from one Philox block
-__device__ __forceinline__ void philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+// four N(0,1) draws from one Philox block (not inlined: ~150 instructions, called from several cold places)
+static __device__ __noinline__ void philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                unsigned long long seed, float out[4]) {
   U4 r = philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
   float u0 = u32_to_unit(r.x), u1 = u32_to_unit(r.y), u2 = u32_to_unit(r.z), u3 = u32_to_unit(r.w);
@@ -124,7 +124,7 @@ __device__ __forceinline__ float activation_f(float x, int act, float slope) {
 }
 
 // processed observation element j of the model input (obs_process_fn), obs points at one row [D]
-__device__ __forceinline__ float proc_obs_elem(const float* obs, int j, int mode, int stride = 1) {
+static __device__ __noinline__ float proc_obs_elem(const float* obs, int j, int mode, int stride = 1) {
   if (mode == B200PETS_PROC_NONE) return obs[j * stride];
   if (mode == B200PETS_PROC_HALFCHEETAH) {  // [o1, sin o2, cos o2, o3:]  (D -> D)
     if (j == 0) return obs[1 * stride];
@@ -140,9 +140,9 @@ __device__ __forceinline__ float proc_obs_elem(const float* obs, int j, int mode
 }
 
 // reward_fn(act, next_obs) -- mbrl/env/reward_fns.py
-__device__ __forceinline__ bool term_eval(int fn, const float* o, int D, int os);
+static __device__ __noinline__ bool term_eval(int fn, const float* o, int D, int os);
 
-__device__ __forceinline__ float reward_eval(int fn, const float* a, int A, int as, const float* o, int D, int os) {
+static __device__ __noinline__ float reward_eval(int fn, const float* a, int A, int as, const float* o, int D, int os) {
   switch (fn) {
     case B200PETS_REWARD_CARTPOLE:
       return term_eval(B200PETS_TERM_CARTPOLE, o, D, os) ? 0.0f : 1.0f;
@@ -179,7 +179,7 @@ __device__ __forceinline__ float reward_eval(int fn, const float* a, int A, int 
 }
 
 // termination_fn(act, next_obs) -- mbrl/env/termination_fns.py
-__device__ __forceinline__ bool term_eval(int fn, const float* o, int D, int os) {
+static __device__ __noinline__ bool term_eval(int fn, const float* o, int D, int os) {
   switch (fn) {
     case B200PETS_TERM_CARTPOLE: {
       float x = o[0], th = o[2 * os];

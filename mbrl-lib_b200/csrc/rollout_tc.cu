@@ -28,6 +28,7 @@ struct TcPlan {
   uint32_t off_A, off_ring, off_obs, off_act, off_const, off_bar;
   uint32_t tmem_cols;
   int obs_ld, act_ld;
+  int h0n;  // columns of the first N half of the hidden layers
   uint32_t smem_bytes;
 };
 
@@ -56,15 +57,70 @@ __device__ __forceinline__ float act_tc(float x, float slope) {
 // byte offset of the 16-byte chunk (row i, k-chunk kc) in the A tile: [kc][i / 8][i % 8][8 x bf16]
 __device__ __forceinline__ uint32_t a_chunk_off(int i, int kc) { return (uint32_t)((kc * 16 + (i >> 3)) * 128 + (i & 7) * 16); }
 
+
+// layer-0 operand of one step -> activation buffer in TMEM: normalise(cat(proc(obs), act)), two constant-one bias
+// columns, zero pad.  Branch-free for obs_process == NONE (clamped loads + selects), generic otherwise.  Not inlined:
+// executed once per horizon step, and the kernel's code size matters (instruction cache).
+static __device__ __noinline__ void build_input_tmem(const ModelDev& m, const float* my_obs, const float* arow,
+                                                     const float* c_mean, const float* c_istd, uint32_t a_out, int cs,
+                                                     int CS, uint64_t* bar_ar) {
+  const int Kp0 = m.Kp[0];
+  for (int ks = cs; ks < Kp0 / 16; ks += CS) {
+    float x[16];
+    if (m.obs_process == B200PETS_PROC_NONE) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int j = ks * 16 + e;
+        const int jo = min(j, m.D - 1), ja = min(max(j - m.Dp, 0), m.A - 1), jc = min(j, m.in - 1);
+        const float vo = my_obs[jo], va = arow[ja];
+        const float v = ((j < m.Dp ? vo : va) - c_mean[jc]) * c_istd[jc];
+        x[e] = j < m.in ? v : (j < m.in + 2 ? 1.f : 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int j = ks * 16 + e;
+        float v;
+        if (j < m.Dp) {
+          v = (proc_obs_elem(my_obs, j, m.obs_process) - c_mean[j]) * c_istd[j];
+        } else if (j < m.in) {
+          v = (arow[j - m.Dp] - c_mean[j]) * c_istd[j];
+        } else {
+          v = (j < m.in + 2) ? 1.f : 0.f;
+        }
+        x[e] = v;
+      }
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(x[2 * e], x[2 * e + 1]);
+    tmem_st8(a_out + (uint32_t)(8 * ks), pk);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  mbar_arrive(&bar_ar[0]);
+  mbar_arrive(&bar_ar[1]);
+}
+
 // CS = column splits of the epilogue: 4 * CS epilogue warps; warp (q, cs) owns TMEM lane quadrant q (rows
 // 32q..32q+31) and every CS-th 16-column chunk.  Thread (row i, cs == 0) also owns the row's scalar state.
+//
+// Data flow of one layer (v3): the A operand (activations, bf16 pairs) lives in TMEM, written by the epilogue with
+// tcgen05.st and consumed by tcgen05.mma in its A-from-TMEM form; weights stream through the shared-memory ring.
+// Hidden layers are split in two N halves so that the epilogue of half 0 runs under the MMAs of half 1, and the next
+// layer's first K steps (which only read half 0's activations) run under the epilogue of half 1:
+//
+//   MMA   : [l.h0 K0-6][l.h0 K7-12] [l.h1 K0-12]        [l+1.h0 K0-6] ..wait.. [l+1.h0 K7-12][l+1.h1 ...
+//   EPI   :                         [epi l.h0 -> A' cols 0-111]  [epi l.h1 -> A' cols 112-207]  [epi l+1.h0 ...
+//
+// TMEM columns: [0, 256) accumulators (hidden: halves at 0 and h0n; output layer at 0), [256, 384) and [384, 512)
+// the two activation buffers (layer g reads buffer g & 1 and its epilogue writes buffer (g + 1) & 1).
 template <int ACT, int CS>
 __global__ void __launch_bounds__(64 + 128 * CS, 1)
 rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const long long num_tiles) {
   constexpr int kEpiThreads = 128 * CS;
   constexpr int kThreadsAll = 64 + kEpiThreads;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* A_s = smem + p.off_A;
   uint8_t* ring = smem + p.off_ring;
   float* obs_s = reinterpret_cast<float*>(smem + p.off_obs);
   float* act_s = reinterpret_cast<float*>(smem + p.off_act);
@@ -76,9 +132,9 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
   float* rew_s = c_nodelta + m.D;      // [128] learned-reward column of the current step
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* bar_empty = bar_full + kMaxStages;
-  uint64_t* bar_a_ready = bar_empty + kMaxStages;
-  uint64_t* bar_acc = bar_a_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
+  uint64_t* bar_ar = bar_empty + kMaxStages;  // [2] activations of half h written (count: all epilogue threads)
+  uint64_t* bar_acc = bar_ar + 2;             // [2] accumulator of half h complete (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.nstages;
@@ -88,20 +144,28 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    mbar_init(bar_a_ready, kEpiThreads);
-    mbar_init(bar_acc, 1);
+    mbar_init(&bar_ar[0], kEpiThreads);
+    mbar_init(&bar_ar[1], kEpiThreads);
+    mbar_init(&bar_acc[0], 1);
+    mbar_init(&bar_acc[1], 1);
     mbar_fence_init();
   }
   for (int j = threadIdx.x; j < m.in; j += kThreadsAll) {
     c_mean[j] = m.norm_mode ? m.norm_mean_f[j] : 0.f;
     c_istd[j] = m.norm_mode ? m.norm_istd_f[j] : 1.f;
   }
+  // logvar clamp folded into two per-output constants (see the output-layer epilogue):
+  //   var = exp(min + softplus(max - softplus(max - lv) - min)) = exp(min) * (1 + exp(max - min) / (1 + exp(max - lv)))
+  float* c_sdmin = c_minlv;  // exp(0.5 * min_logvar)
+  float* c_ratio = c_nodelta + m.D + kTileM;  // exp(max_logvar - min_logvar)
   for (int j = threadIdx.x; j < m.out; j += kThreadsAll) {
-    c_minlv[j] = m.deterministic ? 0.f : m.min_lv[j];
-    c_maxlv[j] = m.deterministic ? 0.f : m.max_lv[j];
+    const float mn = m.deterministic ? 0.f : m.min_lv[j], mx = m.deterministic ? 0.f : m.max_lv[j];
+    c_sdmin[j] = expf(0.5f * mn);
+    c_maxlv[j] = mx;
+    c_ratio[j] = expf(mx - mn);
   }
   for (int j = threadIdx.x; j < m.D; j += kThreadsAll) c_nodelta[j] = (!m.target_is_delta || m.no_delta[j]) ? 1.f : 0.f;
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -111,6 +175,12 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
   const long long Bm = shuffle ? 0 : a.B / m.M;
   const int tpm = shuffle ? 1 : (int)((Bm + kTileM - 1) / kTileM);
   const int nlayers = p.nlayers;
+  const int L = nlayers - 1;         // index of the output layer
+  const int NpH = m.Np[0];           // padded hidden width
+  const int h0n = p.h0n;             // columns of N half 0 (multiple of 16)
+  const int c0 = h0n >> 4;           // 16-column chunks (= K steps of the next layer) in half 0
+  const int NpF = m.Np[L];
+  const bool final_early = NpF <= h0n;  // output accumulator fits in half 0's columns: may start under epilogue h1
 
   if (warp == 0) {
     // =========================== weight producer ===========================
@@ -123,25 +193,16 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           const int mem = shuffle ? shuffle_member(a, (int)tile, t, m.M) : member;
           const uint8_t* base = m.img + (size_t)(blockIdx.x % m.img_replicas) * m.img_replica_stride + (size_t)mem * m.img_member_stride;
           for (int l = 0; l < nlayers; ++l) {
+            // one ring slot holds the whole layer image (K core columns contiguous): one barrier, one wait per layer
             const uint8_t* lsrc = base + m.img_layer_off[l];
-            const uint32_t col_bytes = (uint32_t)m.Np[l] * 16u;  // one K core column (8 K-rows x Np)
-            for (int j = 0; j < p.nblk[l]; ++j) {
-              const int kb = min(64, m.Kp[l] - 64 * j);
-              const int ncol = kb >> 3;
-              const uint32_t bytes = (uint32_t)ncol * col_bytes;
-              mbar_wait(&bar_empty[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&bar_full[stage], bytes);
-              uint8_t* dst = ring + (size_t)stage * p.stage_bytes;
-              const uint8_t* src = lsrc + (size_t)64 * j * m.Np[l] * 2;
-              // the columns of a stage may land in any order: start at a CTA-dependent column so that CTAs streaming
-              // the same member do not walk the same L2 lines in lockstep
-              int c = (int)((blockIdx.x >> 3) % ncol);
-              for (int q = 0; q < ncol; ++q) {
-                bulk_g2s(dst + (size_t)c * col_bytes, src + (size_t)c * col_bytes, col_bytes, &bar_full[stage]);
-                if (++c == ncol) c = 0;
-              }
-              if (++stage == S) { stage = 0; phase ^= 1u; }
-            }
+            const uint32_t bytes = (uint32_t)m.Kp[l] * m.Np[l] * 2u;
+            mbar_wait(&bar_empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&bar_full[stage], bytes);
+            uint8_t* dst = ring + (size_t)stage * p.stage_bytes;
+            const uint32_t piece = ((bytes / 4u) + 127u) & ~127u;  // four copies in flight
+            for (uint32_t off = 0; off < bytes; off += piece)
+              bulk_g2s(dst + off, lsrc + off, min(piece, bytes - off), &bar_full[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -149,45 +210,82 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     __syncwarp();
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // The whole warp runs the control flow converged (waits are uniform); the MMAs and commits are issued by the one
+    // elected lane, always the same one, so that every tcgen05.commit tracks all MMAs issued before it.
+    {
       int stage = 0;
-      uint32_t phase = 0, a_par = 0;
-      const uint32_t A_addr = smem_u32(A_s);
+      uint32_t phase = 0, ar_par = 0;
+      uint32_t g = 0;  // global layer counter: selects the activation buffer
       const uint32_t ring_addr = smem_u32(ring);
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int t = a.t0; t < a.t1; ++t) {
-          for (int l = 0; l < nlayers; ++l) {
+          for (int l = 0; l < nlayers; ++l, ++g) {
+            const bool stamp = a.timeline && lane == 0 && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x;
+            const int nk = m.Kp[l] >> 4;
+            const bool hidden = l < L;
             const uint32_t np = (uint32_t)m.Np[l];
-            const uint32_t idesc = umma_idesc_bf16_m128(np);
             const uint32_t b_lbo = np * 16u;
-            const bool stamp = a.timeline && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x;
+            const uint32_t a_col = tmem_base + 256u + ((g & 1u) << 7);
+            const uint32_t slot_addr = ring_addr + (uint32_t)stage * p.stage_bytes;
+            const uint32_t slot_phase = phase;
+            uint64_t* slot_empty = &bar_empty[stage];
+            uint64_t* slot_full = &bar_full[stage];
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+            const int n0 = hidden ? h0n : NpF;
+            const uint32_t idesc0 = umma_idesc_bf16_m128((uint32_t)n0);
+            const int ksplit = (l == 0) ? nk : min(nk, c0);  // K steps whose activations arrive with half 0
+            const uint64_t b_inc = (uint64_t)((2u * b_lbo) >> 4);  // descriptor start-address step per K step
             if (stamp) a.timeline[64 + l * 4 + 0] = clock64();
-            mbar_wait(bar_a_ready, a_par);
-            a_par ^= 1u;
+            mbar_wait(slot_full, slot_phase);
+            mbar_wait(&bar_ar[0], ar_par);
+            if (!hidden && !final_early) mbar_wait(&bar_ar[1], ar_par);
             tc_fence_after();
             if (stamp) a.timeline[64 + l * 4 + 1] = clock64();
-            for (int j = 0; j < p.nblk[l]; ++j) {
-              const int kb = min(64, m.Kp[l] - 64 * j);
-              mbar_wait(&bar_full[stage], phase);
-              tc_fence_after();
-              if (stamp && j == p.nblk[l] - 1) a.timeline[64 + l * 4 + 2] = clock64();
-              const uint32_t b_addr = ring_addr + (uint32_t)stage * p.stage_bytes;
-              for (int kk = 0; kk < kb / 16; ++kk) {
-                const uint32_t k0 = (uint32_t)(64 * j + 16 * kk);
-                const uint64_t adesc = umma_smem_desc(A_addr + (k0 >> 3) * 2048u, 2048u, 128u);
-                const uint64_t bdesc = umma_smem_desc(b_addr + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128u);
-                umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (j | kk) != 0 ? 1u : 0u);
+            uint64_t bdesc = umma_smem_desc(slot_addr, b_lbo, 128u);
+            if (elect_one()) {
+              uint64_t bd = bdesc;
+              uint32_t acol = a_col;
+              for (int kk = 0; kk < ksplit; ++kk) {
+                umma_bf16_ts(tmem_base, acol, bd, idesc0, kk != 0 ? 1u : 0u);
+                bd += b_inc;
+                acol += 8u;
               }
-              umma_commit(&bar_empty[stage]);
-              if (++stage == S) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(bar_acc);
+            __syncwarp();
+            if (hidden || final_early) {
+              mbar_wait(&bar_ar[1], ar_par);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              uint64_t bd = bdesc + (uint64_t)ksplit * b_inc;
+              uint32_t acol = a_col + 8u * (uint32_t)ksplit;
+              for (int kk = ksplit; kk < nk; ++kk) {
+                umma_bf16_ts(tmem_base, acol, bd, idesc0, 1u);
+                bd += b_inc;
+                acol += 8u;
+              }
+              umma_commit(&bar_acc[0]);
+              if (hidden) {
+                const uint32_t idesc1 = umma_idesc_bf16_m128((uint32_t)(NpH - h0n));
+                bd = umma_smem_desc(slot_addr + (uint32_t)(h0n >> 3) * 128u, b_lbo, 128u);  // weight rows h0n..
+                acol = a_col;
+                const uint32_t d1 = tmem_base + (uint32_t)h0n;
+                for (int kk = 0; kk < nk; ++kk) {
+                  umma_bf16_ts(d1, acol, bd, idesc1, kk != 0 ? 1u : 0u);
+                  bd += b_inc;
+                  acol += 8u;
+                }
+                umma_commit(&bar_acc[1]);
+              }
+              umma_commit(slot_empty);
+            }
+            __syncwarp();
+            ar_par ^= 1u;
             if (stamp) a.timeline[64 + l * 4 + 3] = clock64();
           }
         }
       }
     }
-    __syncwarp();
   } else {
     // =========================== epilogue ===========================
     const int q = warp & 3;            // TMEM lane quadrant this warp may access (hardware: warp id % 4)
@@ -196,11 +294,18 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     const bool owner = cs == 0;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* my_obs = obs_s + i * p.obs_ld;
-    float* my_act = act_s + i * p.act_ld;
-    uint32_t acc_par = 0;
+    float* act_s1 = act_s + kTileM * p.act_ld;  // actions are double buffered by step parity
+    uint32_t acc0_par = 0, acc1_par = 0;
+    uint32_t g = 0;
     const int Kp0 = m.Kp[0];
     const int ngroups = (m.out + 3) >> 2;
+    const bool draw = !m.deterministic && a.sample;
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
+
+    auto build_input = [&](int tt) {
+      build_input_tmem(m, my_obs, ((tt & 1) ? act_s1 : act_s) + i * p.act_ld, c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs,
+                       CS, bar_ar);
+    };
 
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       long long slot0;
@@ -218,8 +323,12 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
       const long long rid = valid ? slot_to_rid(a, slot0 + i) : 0;
       float tot = 0.f;
       int dead = 0;
+      const float* act_row = a.act + (rid / a.act_div) * a.act_row_stride;
+      const bool act_regs = m.A <= 8;  // next-step actions prefetched into registers (hidden behind the layers)
+      float an[8];
       epi_bar();  // previous tile fully consumed before its row state is overwritten
       if (owner) {
+#pragma unroll 1
         for (int d = 0; d < m.D; ++d) {
           float v = 0.f;
           if (valid) v = a.init_from_obs0 ? a.obs0[d] : a.obs_in[rid * m.D + d];
@@ -229,161 +338,170 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           tot = a.total_state[rid];
           dead = a.dead_state[rid];
         }
-      }
-      const float* act_row = a.act + (rid / a.act_div) * a.act_row_stride;
-      const bool act_regs = m.A <= 8;  // next-step actions prefetched into registers (hidden behind the layers)
-      float an[8];
-      if (owner) {
         const float* ap = act_row + (long long)a.t0 * a.act_t_stride;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) an[j] = (valid && j < m.A) ? ap[j] : 0.f;
+        float* arow = ((a.t0 & 1) ? act_s1 : act_s) + i * p.act_ld;
+#pragma unroll 1
+        for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
       }
+      epi_bar();
+      build_input(a.t0);
 
       for (int t = a.t0; t < a.t1; ++t) {
         const bool stamp = a.timeline && blockIdx.x == 0 && warp == 2 && lane == 0 && t == a.t0 + 5 && tile == blockIdx.x;
         int sp = 0;
-        if (stamp) a.timeline[sp++] = clock64();  // 0: step start
-        if (owner) {
-          if (act_regs) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < m.A) my_act[j] = an[j];
-          } else {
-            const float* ap = act_row + (long long)t * a.act_t_stride;
-            for (int j = 0; j < m.A; ++j) my_act[j] = valid ? ap[j] : 0.f;
-          }
-        }
-        epi_bar();
-        if (stamp) a.timeline[sp++] = clock64();  // 1: actions loaded + barrier
-        // ---- layer-0 operand: normalise(cat(proc(obs), act)), two constant-one bias columns, zero pad ----
-        for (int kc = cs; kc < Kp0 / 8; kc += CS) {
-          float x[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int j = kc * 8 + e;
-            float v;
-            if (j < m.Dp) {
-              v = proc_obs_elem(my_obs, j, m.obs_process);
-              v = (v - c_mean[j]) * c_istd[j];
-            } else if (j < m.in) {
-              v = (my_act[j - m.Dp] - c_mean[j]) * c_istd[j];
-            } else {
-              v = (j < m.in + 2) ? 1.f : 0.f;
-            }
-            x[e] = v;
-          }
-          uint4 pk = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-          *reinterpret_cast<uint4*>(A_s + a_chunk_off(i, kc)) = pk;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(bar_a_ready);
-        if (stamp) a.timeline[sp++] = clock64();  // 2: input built
-        // work hidden behind the first MMAs: next step's actions (global loads) and this step's model noise
-        if (owner && act_regs && t + 1 < a.t1) {
+        if (stamp) a.timeline[sp++] = clock64();  // 0: step start (layer-0 operand already handed over)
+        const bool more = t + 1 < a.t1;
+        if (owner && act_regs && more) {  // global loads complete under the layers
           const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
 #pragma unroll
           for (int j = 0; j < 8; ++j) an[j] = (valid && j < m.A) ? ap[j] : 0.f;
         }
-        const bool draw = !m.deterministic && a.sample;
         float zpre[2][4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int g = cs + u * CS;
-          if (draw && !a.eps && g < ngroups)
-            philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)g, (uint32_t)a.offset, a.seed, zpre[u]);
-        }
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) zpre[u][e] = 0.f;
 
-        // ---- hidden layers: TMEM accumulator -> activation -> bf16 -> next A operand ----
-        for (int l = 0; l < nlayers - 1; ++l) {
-          const int np = m.Np[l];
+        // ---- hidden layers: accumulator half -> activation -> bf16 pairs -> next layer's A operand in TMEM ----
+        for (int l = 0; l < L; ++l, ++g) {
           const int n_true = m.N[l];
           const int kp_next = m.Kp[l + 1];
-          mbar_wait(bar_acc, acc_par);
-          acc_par ^= 1u;
-          tc_fence_after();
-          if (stamp) a.timeline[sp++] = clock64();  // 3 + 2l: accumulator ready
-          for (int c = cs; c < kp_next / 16; c += CS) {
-            float v[16];
-            if (16 * c < np) {
-              uint32_t r[16];
-              tmem_ld16(t_lane + (uint32_t)(16 * c), r);
-              tmem_ld_wait();
+          const uint32_t a_out = t_lane + 256u + (((g + 1u) & 1u) << 7);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = act_tc<ACT>(__uint_as_float(r[e]), m.leaky);
+          for (int h = 0; h < 2; ++h) {
+            if (h == 0) {
+              mbar_wait(&bar_acc[0], acc0_par);
+              acc0_par ^= 1u;
             } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = 0.f;
+              mbar_wait(&bar_acc[1], acc1_par);
+              acc1_par ^= 1u;
             }
-            if (16 * c + 15 >= n_true && 16 * c <= n_true + 1) {
+            tc_fence_after();
+            if (stamp) a.timeline[sp++] = clock64();  // accumulator half ready
+            const int cbeg = h == 0 ? 0 : c0;
+            const int cend = h == 0 ? c0 : (kp_next >> 4);
+            for (int c = cbeg + cs; c < cend; c += CS) {
+              float v[16];
+              if (16 * c < NpH) {
+                uint32_t r[16];
+                tmem_ld16(t_lane + (uint32_t)(16 * c), r);
+                tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int col = 16 * c + e;
-                if (col == n_true || col == n_true + 1) v[e] = 1.f;
+                for (int e = 0; e < 16; ++e) v[e] = act_tc<ACT>(__uint_as_float(r[e]), m.leaky);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = 0.f;
               }
+              if (16 * c + 15 >= n_true && 16 * c <= n_true + 1) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const int col = 16 * c + e;
+                  if (col == n_true || col == n_true + 1) v[e] = 1.f;
+                }
+              }
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+              tmem_st8(a_out + (uint32_t)(8 * c), pk);
             }
-            uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-            *reinterpret_cast<uint4*>(A_s + a_chunk_off(i, 2 * c)) = p0;
-            *reinterpret_cast<uint4*>(A_s + a_chunk_off(i, 2 * c + 1)) = p1;
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bar_ar[h]);
+            if (stamp) a.timeline[sp++] = clock64();  // activations of this half written
           }
-          tc_fence_before();
-          fence_proxy_async_smem();
-          mbar_arrive(bar_a_ready);
-          if (stamp) a.timeline[sp++] = clock64();  // 4 + 2l: activations written
+          // ---- side work in the gap while the next layer's first accumulator half completes ----
+          if (l < 2) {  // this step's model noise: Philox + Box-Muller for output group cs + l * CS
+            const int gq = cs + l * CS;
+            if (draw && !a.eps && gq < ngroups) {
+              float z4[4];
+              philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) zpre[l & 1][e] = z4[e];
+            }
+          } else if (l == 2 && owner && more) {  // next step's actions -> the other action buffer
+            float* arow = (((t + 1) & 1) ? act_s1 : act_s) + i * p.act_ld;
+            if (act_regs) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < m.A) arow[j] = an[j];
+            } else {
+              const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
+      #pragma unroll 1
+        for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
+            }
+          }
+        }
+        if (L < 3 && owner && more) {  // shallow models: the action hand-over did not fit in a gap above
+          float* arow = (((t + 1) & 1) ? act_s1 : act_s) + i * p.act_ld;
+          const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
+  #pragma unroll 1
+        for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
         }
 
-        // ---- output layer: groups of 4 outputs; Gaussian sample, delta add-back ----
-        mbar_wait(bar_acc, acc_par);
-        acc_par ^= 1u;
+        // ---- output layer: groups of 4 outputs; Gaussian sample, delta add-back (branch-free inner maths) ----
+        mbar_wait(&bar_acc[0], acc0_par);
+        acc0_par ^= 1u;
+        ++g;
         tc_fence_after();
         if (stamp) a.timeline[sp++] = clock64();  // output accumulator ready
-        for (int g = cs; g < ngroups; g += CS) {
+        for (int gq = cs; gq < ngroups; gq += CS) {
           uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
-          tmem_ld4(t_lane + (uint32_t)(4 * g), rm);
-          if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * g), rl);
+          tmem_ld4(t_lane + (uint32_t)(4 * gq), rm);
+          if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rl);
           tmem_ld_wait();
-          float z[4] = {0.f, 0.f, 0.f, 0.f};
-          if (draw && !a.eps) {
-            const int u = (g - cs) / CS;
-            if (u < 2) {
+          const int u = (gq - cs) / CS;
+          if (stamp) a.timeline[40 + 4 * u] = clock64();
+          float pred[4];
+          if (draw) {
+            float z[4];
+            if (a.eps) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int oc = min(4 * gq + e, m.out - 1);
+                z[e] = valid ? a.eps[((size_t)(t - a.t0) * a.B + rid) * m.out + oc] : 0.f;
+              }
+            } else if (u < 2 && u < L) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) z[e] = u == 0 ? zpre[0][e] : zpre[1][e];
             } else {
-              philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)g, (uint32_t)a.offset, a.seed, z);
+              philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z);
             }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int oc = min(4 * gq + e, m.out - 1);
+              const float e1 = __expf(c_maxlv[oc] - __uint_as_float(rl[e]));        // exp(max - lv)   (inf is fine)
+              const float e2 = __fdividef(c_ratio[oc], 1.f + e1);                  // exp(max - min) / (1 + e1)
+              const float sd = c_sdmin[oc] * sqrtf(1.f + e2);                      // sqrt(exp(clamped logvar))
+              pred[e] = fmaf(sd, z[e], __uint_as_float(rm[e]));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pred[e] = __uint_as_float(rm[e]);
           }
+          if (stamp) a.timeline[41 + 4 * u] = (long long)__float_as_uint(pred[0] + pred[1] + pred[2] + pred[3]) * 0 + clock64();
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int o = 4 * g + e;
+            const int o = 4 * gq + e;
             if (o < m.out) {
-              const float mean = __uint_as_float(rm[e]);
-              float pred = mean;
-              if (draw) {
-                float lv = __uint_as_float(rl[e]);
-                const float mx = c_maxlv[o], mn = c_minlv[o];
-                float d1 = mx - lv;
-                lv = mx - (d1 > 20.f ? d1 : __logf(1.f + __expf(d1)));
-                float d2 = lv - mn;
-                lv = mn + (d2 > 20.f ? d2 : __logf(1.f + __expf(d2)));
-                const float sd = __expf(0.5f * lv);
-                const float ev = a.eps ? (valid ? a.eps[((size_t)(t - a.t0) * a.B + rid) * m.out + o] : 0.f) : z[e];
-                pred = fmaf(sd, ev, mean);
-              }
               if (m.learned_rewards && o == m.out - 1) {
-                rew_s[i] = pred;
+                rew_s[i] = pred[e];
               } else {
-                my_obs[o] = c_nodelta[o] != 0.f ? pred : pred + my_obs[o];
+                my_obs[o] = c_nodelta[o] != 0.f ? pred[e] : pred[e] + my_obs[o];
               }
             }
           }
+          if (stamp) a.timeline[42 + 4 * u] = clock64();
         }
         tc_fence_before();
         if (stamp) a.timeline[sp++] = clock64();  // outputs sampled
         epi_bar();
         if (stamp) a.timeline[sp++] = clock64();  // barrier
+        if (more) build_input(t + 1);             // next step's layer 0 starts while the owner scores this step
+        if (stamp) a.timeline[sp++] = clock64();  // next input handed over
         // ---- reward, termination, accumulate: the row's owner thread ----
         if (owner) {
-          float rew = m.learned_rewards ? rew_s[i] : reward_eval(m.reward_fn, my_act, m.A, 1, my_obs, m.D, 1);
+          const float* arow = ((t & 1) ? act_s1 : act_s) + i * p.act_ld;
+          float rew = m.learned_rewards ? rew_s[i] : reward_eval(m.reward_fn, arow, m.A, 1, my_obs, m.D, 1);
           const bool done = term_eval(m.term_fn, my_obs, m.D, 1);
           if (valid) {
             if (a.reward_out) a.reward_out[rid] = rew;
@@ -398,6 +516,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
       // ---- store row state ----
       if (owner && a.store_state && valid) {
         if (a.obs_out)
+#pragma unroll 1
           for (int d = 0; d < m.D; ++d) a.obs_out[rid * m.D + d] = my_obs[d];
         if (a.total_state) a.total_state[rid] = tot;
         if (a.dead_state) a.dead_state[rid] = (uint8_t)dead;
@@ -407,7 +526,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -640,24 +759,27 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
     if (m.Np[l] > 256 || m.Kp[l] > 256) return false;
     p.nblk[l] = (m.Kp[l] + 63) / 64;
     kp_max = max(kp_max, m.Kp[l]);
-    stage = max(stage, (uint32_t)min(64, m.Kp[l]) * m.Np[l] * 2u);
+    stage = max(stage, (uint32_t)m.Kp[l] * m.Np[l] * 2u);
     while (tm < m.Np[l]) tm *= 2;
   }
   p.stage_bytes = (stage + 127u) & ~127u;
-  p.tmem_cols = (uint32_t)tm;
+  p.tmem_cols = 512;
+  (void)tm;
+  p.h0n = ((m.Np[0] / 16 + 1) / 2) * 16;  // e.g. 208 -> 112 + 96
+  if (m.Np[0] - p.h0n < 16) return false;
   p.obs_ld = m.D | 1;
   p.act_ld = m.A | 1;
   uint32_t off = 0;
-  p.off_A = off; off += (uint32_t)kTileM * kp_max * 2;
+  p.off_A = 0;
   p.off_obs = off; off += (uint32_t)kTileM * p.obs_ld * 4;
-  p.off_act = off; off += (uint32_t)kTileM * p.act_ld * 4;
-  p.off_const = off; off += (uint32_t)(2 * m.in + 2 * m.out + m.D + kTileM) * 4;
+  p.off_act = off; off += 2u * (uint32_t)kTileM * p.act_ld * 4;
+  p.off_const = off; off += (uint32_t)(2 * m.in + 3 * m.out + m.D + kTileM) * 4;
   off = (off + 15u) & ~15u;
-  p.off_bar = off; off += (2 * kMaxStages + 2) * 8 + 16;
+  p.off_bar = off; off += (2 * kMaxStages + 4) * 8 + 16;
   off = (off + 127u) & ~127u;
   p.off_ring = off;
   int S = ((int)max_smem - (int)off) / (int)p.stage_bytes;
-  if (S < 2) return false;
+  if (S < 2) return false;  // one layer in use, the next one in flight
   p.nstages = min(S, kMaxStages);
   p.smem_bytes = off + (uint32_t)p.nstages * p.stage_bytes;
   *out = p;

@@ -19,6 +19,7 @@ lib.b200pets_debug_timeline(None)
 b = buf.cpu().tolist()
 t0 = b[0]
 print("epilogue thread stamps (cycles since step start):", [x - t0 for x in b[:20] if x])
+print("fine stamps:", [x - t0 for x in b[40:56] if x])
 for l in range(5):
     s = b[64 + 4 * l: 68 + 4 * l]
     print(f"mma layer {l}: wait_a_start {s[0]-t0}, a_ready {s[1]-t0}, last_stage_full {s[2]-t0}, issued {s[3]-t0}")
