@@ -147,6 +147,7 @@ __global__ void particle_mean_kernel(int N, int P, const float* __restrict__ tot
 // elite selection + refit: one CTA
 // ------------------------------------------------------------------------------------------------------
 constexpr int kSelThreads = 1024;
+constexpr int kSmallN = 2048;  // populations up to this size are ranked by counting in shared memory
 
 __device__ __forceinline__ uint32_t order_key(float v) {
   uint32_t u = __float_as_uint(v);
@@ -215,12 +216,44 @@ __global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArg
     float v = s.values[i * s.vstride];
     if (isnan(v)) s.values[i * s.vstride] = -1e-10f;
   }
+  __syncthreads();
+
+  float bv;
+  int bi;
+  if (n <= kSmallN) {
+    // ---- small populations (the PETS configurations): rank by counting, everything in shared memory ----
+    __shared__ float sv[kSmallN];
+    __shared__ unsigned char sf[kSmallN];
+    for (int i = tid; i < n; i += kSelThreads) sv[i] = s.values[i * s.vstride];
+    if (tid == 0) sh_besti[0] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kSelThreads) {
+      const float vi = sv[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float vj = sv[j];
+        rank += (vj > vi || (vj == vi && j < i)) ? 1 : 0;
+      }
+      sf[i] = rank < k ? 1 : 0;
+      if (rank == 0) sh_besti[0] = i;  // the maximum, lowest index on ties
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kSelThreads) {
+      if (sf[i]) {
+        int pos = 0;
+        for (int j = 0; j < i; ++j) pos += sf[j];
+        s.elite_idx[pos] = i;
+      }
+    }
+    __syncthreads();
+    bi = sh_besti[0];
+    bv = sv[bi];
+  } else {
   if (tid == 0) {
     sh_prefix = 0;
     sh_krem = k;
   }
   __syncthreads();
-
   // ---- radix select of the k-th largest key, most significant byte first ----
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
@@ -267,8 +300,8 @@ __global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArg
   }
 
   // ---- best value: max, lowest index on ties (best_values[0] / elite_idx[0] of topk) ----
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
+  bv = -INFINITY;
+  bi = 0x7fffffff;
   for (int i = tid; i < n; i += kSelThreads) {
     float v = s.values[i * s.vstride];
     if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
@@ -295,6 +328,8 @@ __global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArg
   __syncthreads();
   bv = sh_bestv[0];
   bi = sh_besti[0];
+
+  }
 
   if (s.mode == 1) {  // records [k][1 + dims]
     for (int idx = tid; idx < k * (s.dims + 1); idx += kSelThreads) {

@@ -35,7 +35,7 @@ def gather_records(local_records: torch.Tensor, group=None) -> torch.Tensor:
     """The one collective of an iteration: all ranks' [k, 1 + dims] records, concatenated in rank order."""
     world = dist.get_world_size(group)
     out = torch.empty((world,) + tuple(local_records.shape), dtype=local_records.dtype, device=local_records.device)
-    dist.all_gather_into_tensor(out, local_records.contiguous(), group=group)
+    dist.all_gather([out[r] for r in range(world)], local_records.contiguous(), group=group)  # NCCL and gloo
     return out.view(world * local_records.shape[0], local_records.shape[1])
 
 
