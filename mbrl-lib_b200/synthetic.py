@@ -91,6 +91,10 @@ _register(CaseSpec("pets_halfcheetah_small", obs_dim=18, act_dim=6, obs_process=
 _register(CaseSpec("humanoid_trunc", obs_dim=45, act_dim=17, learned_rewards=True, reward_fn=None,
                    term_fn="humanoid", population=70, horizon=10, particles=5,
                    action_lb=-0.4, action_ub=0.4, obs0_first=1.4))
+# config 3 at the real Humanoid-v4 dims (obs 376, act 17, learned reward): in 393 -> out 754; outside the tensor-core plan
+_register(CaseSpec("humanoid_v4", obs_dim=376, act_dim=17, learned_rewards=True, reward_fn=None,
+                   term_fn="humanoid", population=20, horizon=6, particles=5,
+                   action_lb=-0.4, action_ub=0.4, obs0_first=1.4))
 # config 4: MBPO step, learned rewards
 _register(CaseSpec("mbpo_halfcheetah", obs_dim=17, act_dim=6, learned_rewards=True, reward_fn=None,
                    population=100000, horizon=1, particles=1))

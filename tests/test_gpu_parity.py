@@ -19,7 +19,8 @@ from mbrl_lib_b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
-CONTINUOUS = ["halfcheetah_small", "pets_halfcheetah_small", "humanoid_trunc", "cartpole_pets", "pusher_det", "halfcheetah"]
+CONTINUOUS = ["halfcheetah_small", "pets_halfcheetah_small", "humanoid_trunc", "cartpole_pets", "pusher_det", "halfcheetah",
+              "humanoid_v4"]
 DISCRETE = ["cartpole", "relu_expectation", "hopper_tsinf", "walker_ant"]
 
 
@@ -324,6 +325,33 @@ def test_in_kernel_noise_matches_injected_in_distribution(precision):
     se = max(np.std(r_inj) / np.sqrt(len(r_inj)), 1e-3)
     assert abs(r_inj.mean() - r_rng.mean()) <= 6 * se + 0.02 * abs(r_inj.mean())
     assert 0.7 <= np.std(r_rng) / np.std(r_inj) <= 1.4
+
+
+def test_humanoid_v4_dims_use_fp32_path():
+    """376-dim observations exceed the tensor-core plan (K, N <= 256): precision='auto' must pick the fp32 kernel,
+    and asking for the tensor-core path must fail loudly rather than fall back silently."""
+    spec, arrays, env = make_env("humanoid_v4", "auto")
+    assert env.precision == "f32" and not env.staged.supports_tc()
+    _, _, env_tc = make_env("humanoid_v4", "bf16_tc")
+    inp = syn.make_rollout_inputs(spec)
+    with pytest.raises(NotImplementedError):
+        gpu_returns(env_tc, spec, inp)
+
+
+def test_warm_start_shift_matches_reference_rule():
+    """TrajectoryOptimizer.optimize keeps best.roll(-replan_freq) with the tail reset (trajectory_opt.py:563-567)."""
+    from mbrl_lib_b200 import _lib
+    from oracle import pets_oracle as po
+
+    lib = _lib.load()
+    H, A = 7, 3
+    best = torch.arange(H * A, dtype=torch.float32, device=DEV).view(H, A)
+    init = torch.tensor([0.5, -0.5, 0.25], device=DEV)
+    for replan in (1, 2, 7):
+        prev = torch.empty(H, A, device=DEV)
+        _lib.check(lib.b200pets_shift_solution(H, A, replan, _lib.ptr(best), _lib.ptr(init), _lib.ptr(prev), _lib.stream_ptr()))
+        ref = po.shift_solution(best.cpu(), replan, init.cpu())
+        assert torch.equal(prev.cpu(), ref)
 
 
 def test_agent_act_end_to_end():
