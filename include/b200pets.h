@@ -199,6 +199,17 @@ int b200pets_icem_append_elites(int32_t keep, int32_t horizon, int32_t act_dim, 
                                 const float* end_eps, uint64_t seed, uint64_t offset, float* dst,
                                 void* stream);
 
+/* MPPIOptimizer building blocks (trajectory_opt.py:191-311).
+ * sample: population[n][t] = clip(beta * (mean[t] + noise[n][t]) + (1 - beta) * population[n][t-1]), t = 0 uses
+ *   past_action; noise = N(0,1) truncated to [-2, 2] (z [dev] float[N][H][A] injected or NULL = Philox).
+ * update: NaN -> -1e-10, weights exp(gamma * (v - max v)), mean <- sum(w * population) / (sum w + 1e-10). */
+int b200pets_mppi_sample(int32_t population, int32_t horizon, int32_t act_dim, float beta, const float* mean,
+                         const float* past_action, const float* lower, const float* upper, const float* z,
+                         uint64_t seed, uint64_t offset, float* population_out, void* stream);
+size_t b200pets_mppi_update_workspace_bytes(int32_t population, int32_t dims);
+int b200pets_mppi_update(int32_t population, int32_t dims, float gamma, const float* population_in, float* values,
+                         float* mean_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* TrajectoryOptimizer warm start (trajectory_opt.py:563-567): roll by -replan_freq, fill the tail. */
 int b200pets_shift_solution(int32_t horizon, int32_t act_dim, int32_t replan_freq, const float* best,
                             const float* initial_row, float* previous_solution, void* stream);

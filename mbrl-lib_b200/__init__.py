@@ -7,7 +7,7 @@ __version__ = "0.1.0"
 
 _LAZY = {
     "ModelEnv": "model_env", "StagedModel": "staging",
-    "Agent": "planning", "Optimizer": "planning", "CEMOptimizer": "planning", "ICEMOptimizer": "planning",
+    "Agent": "planning", "Optimizer": "planning", "CEMOptimizer": "planning", "ICEMOptimizer": "planning", "MPPIOptimizer": "planning",
     "TrajectoryOptimizer": "planning", "TrajectoryOptimizerAgent": "planning",
     "create_trajectory_optim_agent_for_model": "planning", "complete_agent_cfg": "planning",
     "GaussianMLP": "models", "OneDTransitionRewardModel": "models", "EnsembleLinearLayer": "models",

@@ -67,6 +67,10 @@ _SIGNATURES = {
                                        C.c_uint64, _P, _P]),
     "b200pets_icem_append_elites": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, C.c_uint64,
                                               C.c_uint64, _P, _P]),
+    "b200pets_mppi_sample": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64,
+                                       _P, _P]),
+    "b200pets_mppi_update_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "b200pets_mppi_update": (C.c_int, [C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P, C.c_size_t, _P]),
     "b200pets_shift_solution": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "b200pets_cem_plan_workspace_bytes": (C.c_size_t, [_P, C.POINTER(RolloutCfg), C.POINTER(CemCfg)]),
     "b200pets_cem_plan": (C.c_int, [_P, C.POINTER(RolloutCfg), C.POINTER(CemCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

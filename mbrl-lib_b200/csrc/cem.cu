@@ -397,6 +397,99 @@ __global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArg
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// MPPI (mbrl/planning/trajectory_opt.py:191-311)
+// ------------------------------------------------------------------------------------------------------
+// beta-smoothed noisy actions, sequential over the horizon (trajectory_opt.py:262-287): one thread per (n, action dim).
+// NB the reference overwrites the variance-scaled population with mean + *unscaled* truncated noise; restated as is.
+__global__ void mppi_sample_kernel(int n, int H, int A, float beta, const float* __restrict__ mean,
+                                   const float* __restrict__ past, const float* __restrict__ lb,
+                                   const float* __restrict__ ub, const float* __restrict__ z, unsigned long long seed,
+                                   unsigned long long offset, float* __restrict__ pop) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * A) return;
+  const int ni = (int)(idx / A), ad = (int)(idx % A);
+  float prev = past[ad];
+  for (int t = 0; t < H; ++t) {
+    const int d = t * A + ad;
+    float zz;
+    if (z) {
+      zz = z[((size_t)ni * H + t) * A + ad];
+    } else {
+      uint32_t attempt = 0;
+      while (true) {
+        float g[4];
+        philox_normal4((uint32_t)ni, (uint32_t)(d >> 2), RNG_STREAM_CEM | attempt, (uint32_t)offset, seed, g);
+        zz = g[d & 3];
+        if ((zz >= -2.0f && zz <= 2.0f) || attempt >= 64) break;
+        ++attempt;
+      }
+      zz = fminf(fmaxf(zz, -2.0f), 2.0f);
+    }
+    const float v = beta * (mean[d] + zz) + (1.0f - beta) * prev;
+    prev = v;  // the recurrence runs on the un-clipped value (clipping happens after the loop in the reference)
+    float c = v > ub[d] ? ub[d] : v;
+    c = c < lb[d] ? lb[d] : c;
+    pop[((size_t)ni * H + t) * A + ad] = c;
+  }
+}
+
+// softmax-weighted mean of the population (trajectory_opt.py:296-309): one CTA
+__global__ void __launch_bounds__(kSelThreads, 1)
+mppi_update_kernel(int n, int dims, float gamma, const float* __restrict__ pop, float* __restrict__ values,
+                   float* __restrict__ mean_out, float* __restrict__ wts, float* __restrict__ partial) {
+  __shared__ float red[32];
+  __shared__ float sh_max, sh_norm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float vmax = -INFINITY;
+  for (int i = tid; i < n; i += kSelThreads) {
+    float v = values[i];
+    if (isnan(v)) { v = -1e-10f; values[i] = v; }
+    vmax = fmaxf(vmax, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if (lane == 0) red[warp] = vmax;
+  __syncthreads();
+  if (tid < 32) {
+    float v = red[tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (tid == 0) sh_max = v;
+  }
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = tid; i < n; i += kSelThreads) {
+    const float w = expf(gamma * (values[i] - sh_max));
+    wts[i] = w;
+    sum += w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (tid < 32) {
+    float v = red[tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tid == 0) sh_norm = v + 1e-10f;
+  }
+  __syncthreads();
+  for (int d = lane; d < dims; d += 32) {
+    float acc = 0.f;
+    for (int i = warp; i < n; i += 32) acc += pop[(size_t)i * dims + d] * wts[i];
+    partial[warp * dims + d] = acc;
+  }
+  __syncthreads();
+  for (int d = tid; d < dims; d += kSelThreads) {
+    float acc = 0.f;
+    for (int w = 0; w < 32; ++w) acc += partial[w * dims + d];
+    mean_out[d] = acc / sh_norm;
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------
@@ -484,6 +577,34 @@ int b200pets_icem_append_elites(int32_t keep, int32_t horizon, int32_t act_dim, 
   int tot = keep * horizon * act_dim;
   icem_append_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       keep, horizon, act_dim, elite, reinterpret_cast<const long long*>(index), shift, mu, var, end_eps, seed, offset, dst);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}
+
+
+int b200pets_mppi_sample(int32_t population, int32_t horizon, int32_t act_dim, float beta, const float* mean,
+                         const float* past_action, const float* lower, const float* upper, const float* z,
+                         uint64_t seed, uint64_t offset, float* population_out, void* stream) {
+  if (population <= 0 || horizon <= 0 || act_dim <= 0) return b200pets_set_error(B200PETS_EINVAL, "mppi_sample: empty population");
+  long long tot = (long long)population * act_dim;
+  mppi_sample_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      population, horizon, act_dim, beta, mean, past_action, lower, upper, z, seed, offset, population_out);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}
+
+size_t b200pets_mppi_update_workspace_bytes(int32_t population, int32_t dims) {
+  return ((size_t)population + (size_t)32 * dims) * sizeof(float) + 256;
+}
+
+int b200pets_mppi_update(int32_t population, int32_t dims, float gamma, const float* population_in, float* values,
+                         float* mean_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (population <= 0 || dims <= 0) return b200pets_set_error(B200PETS_EINVAL, "mppi_update: empty population");
+  if (workspace_bytes < b200pets_mppi_update_workspace_bytes(population, dims))
+    return b200pets_set_error(B200PETS_EINVAL, "mppi_update: workspace too small");
+  float* wts = reinterpret_cast<float*>(workspace);
+  mppi_update_kernel<<<1, kSelThreads, 0, (cudaStream_t)stream>>>(population, dims, gamma, population_in, values, mean_out,
+                                                                  wts, wts + population);
   CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }

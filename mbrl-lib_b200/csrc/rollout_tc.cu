@@ -300,6 +300,9 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     const int Kp0 = m.Kp[0];
     const int ngroups = (m.out + 3) >> 2;
     const bool draw = !m.deterministic && a.sample;
+    // scoring of step t may be deferred into the gap after hidden layer 2 of step t + 1 only if another hidden layer
+    // follows that gap: the output-layer epilogue (which overwrites obs / learned reward) then needs this thread first
+    const bool defer_score = L >= 4;
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
 
     auto build_input = [&](int tt) {
@@ -323,6 +326,19 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
       const long long rid = valid ? slot_to_rid(a, slot0 + i) : 0;
       float tot = 0.f;
       int dead = 0;
+      // reward_fn(act_t, obs_{t+1}), termination, dead mask, accumulate (model_env.py:124-129, 186-188): row owner only
+      auto score = [&](int ts) {
+        const float* arow = ((ts & 1) ? act_s1 : act_s) + i * p.act_ld;
+        float rew = m.learned_rewards ? rew_s[i] : reward_eval(m.reward_fn, arow, m.A, 1, my_obs, m.D, 1);
+        const bool done = term_eval(m.term_fn, my_obs, m.D, 1);
+        if (valid) {
+          if (a.reward_out) a.reward_out[rid] = rew;
+          if (a.done_out) a.done_out[rid] = done ? 1 : 0;
+        }
+        if (dead) rew = 0.f;
+        dead |= done ? 1 : 0;
+        tot += rew;
+      };
       const float* act_row = a.act + (rid / a.act_div) * a.act_row_stride;
       const bool act_regs = m.A <= 8;  // next-step actions prefetched into registers (hidden behind the layers)
       float an[8];
@@ -410,15 +426,19 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
             if (stamp) a.timeline[sp++] = clock64();  // activations of this half written
           }
           // ---- side work in the gap while the next layer's first accumulator half completes ----
-          if (l < 2) {  // this step's model noise: Philox + Box-Muller for output group cs + l * CS
-            const int gq = cs + l * CS;
+          if (l < 2) {  // this step's model noise: Philox + Box-Muller for output group g0 + l * CS
+            const int gq = (CS - 1 - cs) + l * CS;
             if (draw && !a.eps && gq < ngroups) {
               float z4[4];
               philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z4);
 #pragma unroll
               for (int e = 0; e < 4; ++e) zpre[l & 1][e] = z4[e];
             }
-          } else if (l == 2 && owner && more) {  // next step's actions -> the other action buffer
+            // previous step's reward / termination, off the critical path (the owner has no noise group in this gap)
+            if (l == 1 && owner && t > a.t0 && defer_score) score(t - 1);
+          } else if (l == 2 && owner) {
+            if (!more) continue;
+            // next step's actions -> the other action buffer (the one score(t - 1) just finished reading)
             float* arow = (((t + 1) & 1) ? act_s1 : act_s) + i * p.act_ld;
             if (act_regs) {
 #pragma unroll
@@ -444,12 +464,12 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         ++g;
         tc_fence_after();
         if (stamp) a.timeline[sp++] = clock64();  // output accumulator ready
-        for (int gq = cs; gq < ngroups; gq += CS) {
+        for (int gq = CS - 1 - cs; gq < ngroups; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
           uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
           tmem_ld4(t_lane + (uint32_t)(4 * gq), rm);
           if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rl);
           tmem_ld_wait();
-          const int u = (gq - cs) / CS;
+          const int u = (gq - (CS - 1 - cs)) / CS;
           if (stamp) a.timeline[40 + 4 * u] = clock64();
           float pred[4];
           if (draw) {
@@ -498,19 +518,8 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         if (stamp) a.timeline[sp++] = clock64();  // barrier
         if (more) build_input(t + 1);             // next step's layer 0 starts while the owner scores this step
         if (stamp) a.timeline[sp++] = clock64();  // next input handed over
-        // ---- reward, termination, accumulate: the row's owner thread ----
-        if (owner) {
-          const float* arow = ((t & 1) ? act_s1 : act_s) + i * p.act_ld;
-          float rew = m.learned_rewards ? rew_s[i] : reward_eval(m.reward_fn, arow, m.A, 1, my_obs, m.D, 1);
-          const bool done = term_eval(m.term_fn, my_obs, m.D, 1);
-          if (valid) {
-            if (a.reward_out) a.reward_out[rid] = rew;
-            if (a.done_out) a.done_out[rid] = done ? 1 : 0;
-          }
-          if (dead) rew = 0.f;
-          dead |= done ? 1 : 0;
-          tot += rew;
-        }
+        // ---- reward, termination, accumulate: deferred into a gap of the next step when the model is deep enough ----
+        if (owner && !(more && defer_score)) score(t);
         if (stamp) a.timeline[sp++] = clock64();  // reward done
       }
       // ---- store row state ----

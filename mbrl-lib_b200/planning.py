@@ -269,7 +269,56 @@ class ICEMOptimizer(Optimizer):
         return out.view(H, A).clone()
 
 
-_KNOWN_TARGETS = {"CEMOptimizer": CEMOptimizer, "ICEMOptimizer": ICEMOptimizer}
+
+class MPPIOptimizer(Optimizer):
+    """Model Predictive Path Integral optimiser, trajectory_opt.py:191-311 (constructor kwargs of mppi.yaml)."""
+
+    def __init__(self, num_iterations: int, population_size: int, gamma: float, sigma: float, beta: float,
+                 lower_bound: Sequence[Sequence[float]], upper_bound: Sequence[Sequence[float]], device):
+        super().__init__()
+        self.planning_horizon = len(lower_bound)
+        self.population_size = population_size
+        self.action_dimension = len(lower_bound[0])
+        self.device = torch.device(device)
+        self.mean = torch.zeros((self.planning_horizon, self.action_dimension), device=self.device, dtype=torch.float32)
+        self.lower_bound = torch.tensor(lower_bound, device=self.device, dtype=torch.float32).contiguous()
+        self.upper_bound = torch.tensor(upper_bound, device=self.device, dtype=torch.float32).contiguous()
+        self.var = sigma ** 2 * torch.ones_like(self.lower_bound)  # kept for API parity; unused by the reference's sampler
+        self.beta = beta
+        self.gamma = gamma
+        self.refinements = num_iterations
+        self.lib = _lib.load()
+        self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+
+    def optimize(self, obj_fun, x0: Optional[torch.Tensor] = None, callback=None, *, _noise=None, **kwargs) -> torch.Tensor:
+        H, A, N = self.planning_horizon, self.action_dimension, self.population_size
+        dev = self.device
+        # `past_action = self.mean[0]` is a view in the reference and the in-place shift below rewrites it: the value
+        # used by every refinement is the *shifted* first row (old mean[1]); restated explicitly (lines 250-251).
+        self.mean[:-1] = self.mean[1:].clone()
+        past_action = self.mean[0].clone()
+        pop = torch.empty(N, H, A, device=dev)
+        nbytes = self.lib.b200pets_mppi_update_workspace_bytes(N, H * A)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        stream = _lib.stream_ptr()
+        base = _next_seed_offset(self) * 1024
+        with torch.cuda.device(dev):
+            for k in range(self.refinements):
+                z = None if _noise is None else _noise[k].to(dev, torch.float32).contiguous()
+                _lib.check(self.lib.b200pets_mppi_sample(N, H, A, float(self.beta), _lib.ptr(self.mean), _lib.ptr(past_action),
+                                                         _lib.ptr(self.lower_bound), _lib.ptr(self.upper_bound), _lib.ptr(z),
+                                                         self._seed, base + k, _lib.ptr(pop), stream), "mppi_sample")
+                values = obj_fun(pop).to(dev, torch.float32).contiguous()
+                new_mean = torch.empty(H, A, device=dev)
+                _lib.check(self.lib.b200pets_mppi_update(N, H * A, float(self.gamma), _lib.ptr(pop), _lib.ptr(values),
+                                                         _lib.ptr(new_mean), _lib.ptr(ws), nbytes, stream), "mppi_update")
+                if callback is not None:
+                    callback(pop, values, k)
+                self.mean = new_mean
+        return self.mean.clone()
+
+
+_KNOWN_TARGETS = {"CEMOptimizer": CEMOptimizer, "ICEMOptimizer": ICEMOptimizer, "MPPIOptimizer": MPPIOptimizer}
 
 
 def _cfg_to_dict(cfg) -> dict:

@@ -239,6 +239,27 @@ def gen_icem():
     print("icem", sols[1][0].tolist())
 
 
+def gen_mppi():
+    g = np.random.default_rng(99)
+    N, H, A, iters = 48, 6, 2, 3
+    lb = torch.tensor(np.tile([-1.0, -0.5], (H, 1)), dtype=torch.float32)
+    ub = torch.tensor(np.tile([1.0, 0.5], (H, 1)), dtype=torch.float32)
+    target = torch.tensor(g.uniform(-0.4, 0.4, (H, A)).astype(np.float32))
+    opt = mbrl.planning.MPPIOptimizer(iters, N, 0.9, 0.5, 0.7, lb.tolist(), ub.tolist(), "cpu")
+    out = {}
+    for call in range(2):
+        z = np.clip(g.standard_normal((iters, N, H, A)), -2, 2).astype(np.float32)
+        trace = []
+        with FeedRNG(truncs=[torch.from_numpy(z[k]) for k in range(iters)]):
+            sol = opt.optimize(quad_objective(target), callback=lambda p, v, k: trace.append((p.clone(), v.clone())))
+        out[f"z{call}"] = z
+        out[f"sol{call}"] = sol.numpy()
+        out[f"pops{call}"] = np.stack([t[0].numpy() for t in trace])
+    np.savez(os.path.join(GOLD, "mppi.npz"), lb=lb.numpy(), ub=ub.numpy(), target=target.numpy(), iters=iters, N=N,
+             gamma=0.9, sigma=0.5, beta=0.7, **out)
+    print("mppi", out["sol1"][0].tolist())
+
+
 def gen_cem_model():
     """Full CEM over the model rollout (small halfcheetah case): pins optimiser+rollout composition."""
     spec = syn.CASES["halfcheetah_small"]
@@ -275,4 +296,5 @@ if __name__ == "__main__":
     gen_cem("trunc_mean", clipped=False, return_mean=True)
     gen_cem("clipped_best", clipped=True, return_mean=False)
     gen_icem()
+    gen_mppi()
     gen_cem_model()

@@ -373,6 +373,33 @@ def icem_optimize(obj_fun, x0, lb, ub, num_iterations, elite_ratio, population_s
     return (mu if return_mean_elites else best_sol), elite
 
 
+def mppi_optimize(obj_fun, mean, lb, ub, num_iterations, population_size, gamma, beta, noise, trace=None):
+    """MPPIOptimizer.optimize (trajectory_opt.py:233-311).  ``mean`` [H,A] is the optimiser's state (returned updated);
+    ``noise[k]`` [N,H,A] are the (already truncated) N(0,1) draws of refinement k.  Note two quirks restated as is:
+    ``past_action`` aliases mean[0] and therefore holds the *shifted* row, and the variance-scaled population is
+    overwritten by mean + unscaled noise."""
+    mean = mean.clone()
+    mean[:-1] = mean[1:].clone()
+    past_action = mean[0].clone()
+    H = mean.shape[0]
+    for k in range(num_iterations):
+        nz = noise[k]
+        pop = torch.empty_like(nz)
+        pop[:, 0, :] = beta * (mean[0, :] + nz[:, 0, :]) + (1 - beta) * past_action
+        for i in range(max(H - 1, 0)):
+            pop[:, i + 1, :] = beta * (mean[i + 1] + nz[:, i + 1, :]) + (1 - beta) * pop[:, i, :]
+        pop = torch.where(pop > ub, ub, pop)
+        pop = torch.where(pop < lb, lb, pop)
+        vals = obj_fun(pop, k).clone()
+        vals[vals.isnan()] = -1e-10
+        w = torch.reshape(torch.exp(gamma * (vals - vals.max())), (population_size, 1, 1))
+        norm = torch.sum(w) + 1e-10
+        mean = torch.sum(pop * w, dim=0) / norm
+        if trace is not None:
+            trace.append({"pop": pop, "values": vals, "mean": mean.clone()})
+    return mean
+
+
 def shift_solution(best, replan_freq, initial_row):
     """TrajectoryOptimizer.optimize warm start (trajectory_opt.py:563-567)."""
     prev = best.roll(-replan_freq, dims=0)

@@ -259,6 +259,21 @@ def test_icem_optimizer_matches_reference(golden_dir):
         np.testing.assert_allclose(ours, theirs, rtol=1e-4, atol=2e-5)
 
 
+def test_mppi_optimizer_matches_reference(golden_dir):
+    import mbrl_lib_b200 as bp
+
+    g = np.load(os.path.join(golden_dir, "mppi.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(DEV)  # noqa: E731
+    opt = bp.MPPIOptimizer(int(g["iters"]), int(g["N"]), float(g["gamma"]), float(g["sigma"]), float(g["beta"]),
+                           g["lb"].tolist(), g["ub"].tolist(), DEV)
+    for call in range(2):  # the second call exercises the shifted mean / past action
+        trace = []
+        sol = opt.optimize(_quad(t("target")), callback=lambda p, v, k: trace.append(p.clone()), _noise=t(f"z{call}"))
+        for k, p in enumerate(trace):
+            np.testing.assert_allclose(p.cpu().numpy(), g[f"pops{call}"][k], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(sol.cpu().numpy(), g[f"sol{call}"], rtol=1e-4, atol=1e-5)
+
+
 @pytest.mark.parametrize("precision,tol", [("f32", 5e-4), ("bf16_tc", 3e-2)])
 def test_fused_cem_plan_matches_reference(golden_dir, precision, tol):
     """CEMOptimizer.optimize over ModelEnv.evaluate_action_sequences as ONE C call, injected noise."""

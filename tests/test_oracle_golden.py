@@ -91,6 +91,20 @@ def test_icem_matches_reference(golden_dir):
         np.testing.assert_allclose(elite.numpy(), g[f"c{call}_elite"], rtol=1e-5, atol=1e-6)
 
 
+def test_mppi_matches_reference(golden_dir):
+    g = _load(golden_dir, "mppi.npz")
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    H, A = g["lb"].shape
+    mean = torch.zeros(H, A)
+    for call in range(2):
+        trace = []
+        mean = po.mppi_optimize(_quad(t("target")), mean, t("lb"), t("ub"), int(g["iters"]), int(g["N"]), float(g["gamma"]),
+                                float(g["beta"]), t(f"z{call}"), trace=trace)
+        for k, tr in enumerate(trace):
+            np.testing.assert_allclose(tr["pop"].numpy(), g[f"pops{call}"][k], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(mean.numpy(), g[f"sol{call}"], rtol=1e-6, atol=1e-7)
+
+
 def test_cem_over_model_matches_reference(golden_dir):
     g = _load(golden_dir, "cem_model.npz")
     spec = syn.CASES["halfcheetah_small"]
