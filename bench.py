@@ -136,8 +136,10 @@ def run_ours(args):
 
         opt = ShardedCEMOptimizer(CEM_ITERS, ELITE_RATIO, N * world, lb, ub, ALPHA, device, return_mean_elites=True)
 
+        obj = _FusedObjective(env, obs0, P)
+
         def step():
-            return opt.optimize(lambda pop: env.evaluate_action_sequences(pop, obs0, P), x0=x0)
+            return opt.optimize(obj, x0=x0)
         launches_per_step = CEM_ITERS * 5  # sample, rollout, particle mean, local top-k, refit-from-records
 
     def barrier():
@@ -204,6 +206,26 @@ def run_ours(args):
         e2e = {"value": CEM_ITERS * N * args.steps / dt, "unit": "sequences/s", "h2d_bytes_per_step": spec.obs_dim * 4,
                "d2h_bytes_per_step": H * A * 4, "ms_per_step": dt / args.steps * 1e3,
                "note": "agent.act(obs): includes the 256 MB L2-flush write between steps"}
+    # ---- population scan of the rollout alone (BASELINE.json config 5 shape, one GPU): fills all SMs ----
+    scan = []
+    if world == 1 and not args.no_scan:
+        peak_tf, _ = measured_peak_tflops()
+        for scale in (2, 8, 32, 128):
+            big = pop.repeat(scale, 1, 1)
+            for _ in range(2):
+                env.evaluate_action_sequences(big, obs0, P)
+            torch.cuda.synchronize()
+            reps = 5
+            ks.record()
+            for _ in range(reps):
+                env.evaluate_action_sequences(big, obs0, P)
+            ke.record()
+            torch.cuda.synchronize()
+            ms = ks.elapsed_time(ke) / reps
+            sps = big.shape[0] / (ms * 1e-3)
+            scan.append({"population": int(big.shape[0]), "ms": ms, "sequences_per_s": sps,
+                         "tensor_roofline_frac": sps * FLOP_PER_SEQ / 1e12 / peak_tf})
+            del big
     clocks = sampler.stop() if rank == 0 else None
 
     cpu = None
@@ -234,6 +256,8 @@ def run_ours(args):
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if scan:
+            line["population_scan_rollout_only"] = scan
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -333,6 +357,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-scan", action="store_true", help="skip the population scan of the rollout kernel")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

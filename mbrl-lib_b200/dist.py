@@ -35,7 +35,10 @@ def gather_records(local_records: torch.Tensor, group=None) -> torch.Tensor:
     """The one collective of an iteration: all ranks' [k, 1 + dims] records, concatenated in rank order."""
     world = dist.get_world_size(group)
     out = torch.empty((world,) + tuple(local_records.shape), dtype=local_records.dtype, device=local_records.device)
-    dist.all_gather([out[r] for r in range(world)], local_records.contiguous(), group=group)  # NCCL and gloo
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out.view(-1), local_records.contiguous().view(-1), group=group)  # one NCCL kernel
+    else:  # gloo (CPU tests)
+        dist.all_gather([out[r] for r in range(world)], local_records.contiguous(), group=group)
     return out.view(world * local_records.shape[0], local_records.shape[1])
 
 
@@ -89,6 +92,19 @@ class ShardedCEMOptimizer:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self._offset += 1
         stream = _lib.stream_ptr()
+        from .planning import _FusedObjective
+
+        fused = obj_fun if isinstance(obj_fun, _FusedObjective) and obj_fun.model_env.ts1 == "tile_shuffle" else None
+        if fused is not None:
+            env = fused.model_env
+            env.staged.ensure_fresh()
+            prop = env._propagation()
+            H = shape[0]
+            rcfg = _lib.RolloutCfg(n_loc, H, fused.num_particles, _lib.PREC[env.precision], _lib.PROP[prop],
+                                   _lib.TS1_TILE_SHUFFLE, (env._seed + 0x9E3779B97F4A7C15 * self.rank) & 0xFFFFFFFFFFFFFFFF, 0)
+            obs0 = env._obs_to_device(fused.obs)
+            values = torch.empty(n_loc, dtype=torch.float32, device=dev)
+            eval_ws = env._workspace(self.lib.b200pets_eval_workspace_bytes(env.staged.handle, C.byref(rcfg)))
         with torch.cuda.device(dev):
             for i in range(self.num_iterations):
                 # rank-distinct Philox stream: offset encodes (call, iteration, rank)
@@ -96,7 +112,13 @@ class ShardedCEMOptimizer:
                 _lib.check(self.lib.b200pets_cem_sample(n_loc, dims, _lib.ptr(mu), _lib.ptr(disp), _lib.ptr(self.lower_bound),
                                                         _lib.ptr(self.upper_bound), None, self._seed, off, 0, _lib.ptr(pop),
                                                         stream), "cem_sample")
-                values = obj_fun(pop).to(dev, torch.float32).contiguous()
+                if fused is not None:  # ModelEnv objective: one C call, no per-iteration host staging
+                    rcfg.offset = env._next_offset()
+                    _lib.check(self.lib.b200pets_eval_sequences(env.staged.handle, C.byref(rcfg), _lib.ptr(obs0), _lib.ptr(pop), None,
+                                                                None, _lib.ptr(values), None, _lib.ptr(eval_ws), eval_ws.numel(),
+                                                                stream), "eval_sequences")
+                else:
+                    values = obj_fun(pop).to(dev, torch.float32).contiguous()
                 if callback is not None:
                     callback(pop, values, i)
                 _lib.check(self.lib.b200pets_cem_local_topk(n_loc, dims, k, _lib.ptr(pop), _lib.ptr(values), _lib.ptr(records),
