@@ -1,6 +1,7 @@
 // C ABI of libb200pets: model staging (pack), rollout dispatch, fused CEM plan.  See include/b200pets.h.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cuda_bf16.h>
@@ -393,7 +394,10 @@ namespace {
 __global__ void cem_init_kernel(int dims, const float* __restrict__ x0, const float* __restrict__ lb,
                                 const float* __restrict__ ub, int clipped, float* mu, float* disp, float* best_value) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d == 0) *best_value = -INFINITY;
+  if (d == 0) {
+    *best_value = -INFINITY;
+    *reinterpret_cast<unsigned int*>(best_value + 1) = 0u;  // tail counter of the fused iteration kernel
+  }
   if (d >= dims) return;
   mu[d] = x0[d];
   const float w = ub[d] - lb[d];
@@ -434,7 +438,56 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
 
   cem_init_kernel<<<(dims + 255) / 256, 256, 0, stream>>>(dims, x0, lower, upper, ccfg->clipped_normal, mu, disp, best_val);
   CUDA_TRY(cudaGetLastError());
+  // Default: sample -> rollout -> particle mean -> refit (4 small launches per iteration, 1.93 ms per 5-iteration plan
+  // at config 2).  B200PETS_CEM_FUSED=1 selects the fused variants, kept because they are parity-tested but measured
+  // SLOWER on B200: refit by the last CTA of the rollout kernel (2 launches / iteration, 2.01 ms) and, with
+  // B200PETS_CEM_SAMPLE_IN_KERNEL=1, the population drawn inside the rollout kernel too (1 launch / iteration,
+  // 2.68 ms: every particle row re-derives its sequence's actions on the epilogue's critical path).
+  const char* env_fuse = getenv("B200PETS_CEM_FUSED");
+  const bool fuse = (env_fuse && env_fuse[0] == '1') && rcfg->precision == B200PETS_PREC_BF16_TC && model->tc_ok && !z &&
+                    !perms && N <= 2048 && dims <= 1024 && ccfg->elite_num >= 2 && ccfg->elite_num <= N &&
+                    rcfg->propagation != B200PETS_PROP_EXPECTATION && B % model->desc.num_members == 0 &&
+                    model->desc.reward_fn != B200PETS_REWARD_EXTERNAL && model->desc.term_fn != B200PETS_TERM_EXTERNAL;
+  const char* env_sik = getenv("B200PETS_CEM_SAMPLE_IN_KERNEL");
+  const bool sample_in_kernel = env_sik && env_sik[0] == '1';
   for (int it = 0; it < ccfg->num_iterations; ++it) {
+    if (fuse) {
+      // default: population drawn by cem_sample_kernel, rollout + refit in one kernel (2 launches per iteration);
+      // B200PETS_CEM_SAMPLE_IN_KERNEL=1 also draws the population inside the rollout kernel (1 launch per iteration,
+      // measured slower: every particle row re-derives its sequence's actions on the epilogue's critical path)
+      if (!sample_in_kernel) {
+        int rcs = b200pets_cem_sample(N, dims, mu, disp, lower, upper, nullptr, rcfg->seed, rcfg->offset * 1024 + it,
+                                      ccfg->clipped_normal, pop, stream);
+        if (rcs) return rcs;
+      }
+      unsigned char* ews = reinterpret_cast<unsigned char*>(eval_ws);
+      const size_t o1 = ((size_t)B * model->desc.obs_dim * sizeof(float) + 255) & ~(size_t)255;
+      RolloutArgs a{};
+      a.N = N; a.H = H; a.P = P; a.B = B;
+      a.t0 = 0; a.t1 = H;
+      a.propagation = rcfg->propagation;
+      a.slot_mode = rcfg->propagation == B200PETS_PROP_RANDOM_MODEL ? 1 : 2;
+      a.sample = 1;
+      a.seed = rcfg->seed; a.offset = rcfg->offset * 1024 + it;
+      a.eps = eps ? eps + (size_t)it * H * B * model->desc.out_size : nullptr;
+      a.obs0 = obs0; a.init_from_obs0 = 1; a.store_state = 1;
+      a.total_state = reinterpret_cast<float*>(ews + o1);
+      a.dead_state = ews + o1 + (((size_t)B * sizeof(float) + 255) & ~(size_t)255);
+      a.act = pop; a.act_div = P; a.act_row_stride = (long long)H * A; a.act_t_stride = A;
+      if (sample_in_kernel) {
+        a.cem_mu = mu; a.cem_disp = disp; a.cem_lb = lower; a.cem_ub = upper;
+        a.cem_offset = rcfg->offset * 1024 + it;
+      }
+      a.cem_clipped = ccfg->clipped_normal;
+      a.pop_out = pop;
+      a.tail_counter = reinterpret_cast<unsigned int*>(best_val + 1);
+      a.tail_values = values; a.tail_mu = mu; a.tail_disp = disp; a.tail_best_value = best_val; a.tail_best_solution = best_sol;
+      a.tail_elite_num = ccfg->elite_num; a.tail_alpha = ccfg->alpha;
+      int rc = dispatch(model, B200PETS_PREC_BF16_TC, a, stream);
+      if (rc) return rc;
+      if (values_out) CUDA_TRY(cudaMemcpyAsync(values_out + (size_t)it * N, values, sizeof(float) * N, cudaMemcpyDeviceToDevice, stream));
+      continue;
+    }
     int rc = b200pets_cem_sample(N, dims, mu, disp, lower, upper, z ? z + (size_t)it * N * dims : nullptr, rcfg->seed,
                                  rcfg->offset * 1024 + it, ccfg->clipped_normal, pop, stream);
     if (rc) return rc;

@@ -64,6 +64,22 @@ struct RolloutArgs {
   float* reward_out;       // [B] or NULL
   uint8_t* done_out;       // [B] or NULL
   long long* timeline;     // diagnostics: clock64 stamps of CTA 0 (b200pets_debug_timeline) or NULL
+  // ---- fused CEM iteration (tensor-core kernel only): population sampled in-kernel, refit by the last CTA ----
+  const float* cem_mu;     // [H*A] sampling mean; non-NULL switches the action source to in-kernel sampling
+  const float* cem_disp;   // [H*A] variance (truncated normal) or std (clipped normal)
+  const float* cem_lb;     // [H*A]
+  const float* cem_ub;     // [H*A]
+  int cem_clipped;
+  unsigned long long cem_offset;  // Philox offset of the population draw (same keying as b200pets_cem_sample)
+  float* pop_out;          // [N][H][A] population, written by each sequence's particle-0 row
+  unsigned int* tail_counter;     // zero-initialised; non-NULL: the last CTA to finish refits (mu, sigma) in place
+  float* tail_values;      // [N] particle-mean returns (out)
+  float* tail_mu;          // [H*A] in/out
+  float* tail_disp;        // [H*A] in/out
+  float* tail_best_value;  // [1] in/out
+  float* tail_best_solution;  // [H*A] in/out
+  int tail_elite_num;
+  float tail_alpha;
 };
 
 // ------------------------------------------------------------------------------------------------------

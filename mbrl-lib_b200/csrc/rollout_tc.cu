@@ -37,6 +37,7 @@ namespace {
 constexpr int kEpiSplit = 4;  // column splits of the epilogue (16 epilogue warps)
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
+constexpr int kCemTabDims = 1024;  // horizon * act_dim supported by the fused CEM iteration
 
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
@@ -102,6 +103,136 @@ static __device__ __noinline__ void build_input_tmem(const ModelDev& m, const fl
   mbar_arrive(&bar_ar[1]);
 }
 
+// Actions of (sequence n, step t) drawn from the CEM sampling distribution with exactly the Philox keying of
+// cem_sample_kernel (cem.cu): element d = t * A + j of sequence n <- block (n, d >> 2, RNG_STREAM_CEM | attempt)[d & 3],
+// redrawn until inside [-2, 2] (util/math.py:83-92) unless clipped_normal.  tab_mu / tab_sd: staged mean and
+// sqrt(constrained variance) (or std for clipped_normal).  Not inlined (cold, once per step per row).
+static __device__ __noinline__ void cem_sample_actions(unsigned long long seed, unsigned long long cem_offset, int clipped,
+                                                       const float* lb, const float* ub, const float* tab_mu,
+                                                       const float* tab_sd, int n, int t, int A, float* dst, float* pop_row) {
+  for (int j0 = 0; j0 < A;) {
+    const int d0 = t * A + j0;
+    const int blk = d0 >> 2;
+    float g[4];
+    philox_normal4((uint32_t)n, (uint32_t)blk, RNG_STREAM_CEM, (uint32_t)cem_offset, seed, g);
+    for (int e = d0 & 3; e < 4 && j0 < A; ++e, ++j0) {
+      const int d = t * A + j0;
+      float zz = g[e];
+      if (!clipped) {
+        uint32_t attempt = 0;
+        while (!(zz >= -2.0f && zz <= 2.0f) && attempt < 64) {
+          ++attempt;
+          float g2[4];
+          philox_normal4((uint32_t)n, (uint32_t)blk, RNG_STREAM_CEM | attempt, (uint32_t)cem_offset, seed, g2);
+          zz = g2[e];
+        }
+        zz = fminf(fmaxf(zz, -2.0f), 2.0f);
+      }
+      float v;
+      if (clipped) {
+        v = tab_mu[d] + tab_sd[d] * zz;
+        v = v > lb[d] ? v : lb[d];
+        v = v < ub[d] ? v : ub[d];
+      } else {
+        v = zz * tab_sd[d] + tab_mu[d];
+      }
+      dst[j0] = v;
+      if (pop_row) pop_row[d] = v;
+    }
+  }
+}
+
+// Refit of (mu, sigma) by the last CTA to finish a fused CEM iteration: particle means, NaN rule, top-k by counting
+// rank (ties -> lowest index), mean / unbiased variance (or std) of the elites, momentum, best-so-far.
+// Same arithmetic as cem_select_kernel (cem.cu) for populations <= 2048; scratch lives in the (now idle) weight ring.
+struct TailArgs {
+  int N, P, tail_elite_num, cem_clipped;
+  float tail_alpha;
+  const float* total_state;
+  const float* pop_out;
+  float *tail_values, *tail_mu, *tail_disp, *tail_best_value, *tail_best_solution;
+  unsigned int* tail_counter;
+};
+
+static __device__ __noinline__ void cem_tail_refit(const TailArgs* ap, int dims, uint8_t* scratch, int* sh_best) {
+  const TailArgs a = *ap;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int n = a.N, k = a.tail_elite_num, P = a.P;
+  float* sv = reinterpret_cast<float*>(scratch);
+  int* eidx = reinterpret_cast<int*>(sv + 2048);
+  unsigned char* sf = reinterpret_cast<unsigned char*>(eidx + 2048);
+  float* partial = reinterpret_cast<float*>(sf + 2048);  // [nwarp + 1][dims]
+  for (int i = tid; i < n; i += nthr) {
+    float s = 0.f;
+    for (int pp = 0; pp < P; ++pp) s += a.total_state[(size_t)i * P + pp];
+    float v = s / (float)P;
+    if (isnan(v)) v = -1e-10f;
+    sv[i] = v;
+    a.tail_values[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nthr) {
+    const float vi = sv[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float vj = sv[j];
+      rank += (vj > vi || (vj == vi && j < i)) ? 1 : 0;
+    }
+    sf[i] = rank < k ? 1 : 0;
+    if (rank == 0) *sh_best = i;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nthr) {
+    if (sf[i]) {
+      int pos = 0;
+      for (int j = 0; j < i; ++j) pos += sf[j];
+      eidx[pos] = i;
+    }
+  }
+  __syncthreads();
+  const int bi = *sh_best;
+  const float bv = sv[bi];
+  const float* pop = a.pop_out;
+  for (int d = lane; d < dims; d += 32) {
+    float acc = 0.f;
+    for (int e = warp; e < k; e += nwarp) acc += pop[(size_t)eidx[e] * dims + d];
+    partial[warp * dims + d] = acc;
+  }
+  __syncthreads();
+  for (int d = tid; d < dims; d += nthr) {
+    float acc = 0.f;
+    for (int w = 0; w < nwarp; ++w) acc += partial[w * dims + d];
+    partial[nwarp * dims + d] = acc / (float)k;
+  }
+  __syncthreads();
+  for (int d = lane; d < dims; d += 32) {
+    const float mean = partial[nwarp * dims + d];
+    float acc = 0.f;
+    for (int e = warp; e < k; e += nwarp) {
+      const float df = pop[(size_t)eidx[e] * dims + d] - mean;
+      acc += df * df;
+    }
+    partial[warp * dims + d] = acc;
+  }
+  __syncthreads();
+  const bool better = bv > *a.tail_best_value;
+  for (int d = tid; d < dims; d += nthr) {
+    float acc = 0.f;
+    for (int w = 0; w < nwarp; ++w) acc += partial[w * dims + d];
+    const float mean = partial[nwarp * dims + d];
+    const float var = acc / (float)(k - 1);
+    const float nd = a.cem_clipped ? sqrtf(var) : var;
+    a.tail_mu[d] = a.tail_alpha * a.tail_mu[d] + (1.0f - a.tail_alpha) * mean;
+    a.tail_disp[d] = a.tail_alpha * a.tail_disp[d] + (1.0f - a.tail_alpha) * nd;
+    if (better) a.tail_best_solution[d] = pop[(size_t)bi * dims + d];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (better) *a.tail_best_value = bv;
+    *a.tail_counter = 0u;  // ready for the next iteration's launch
+  }
+}
+
 // CS = column splits of the epilogue: 4 * CS epilogue warps; warp (q, cs) owns TMEM lane quadrant q (rows
 // 32q..32q+31) and every CS-th 16-column chunk.  Thread (row i, cs == 0) also owns the row's scalar state.
 //
@@ -115,7 +246,7 @@ static __device__ __noinline__ void build_input_tmem(const ModelDev& m, const fl
 //
 // TMEM columns: [0, 256) accumulators (hidden: halves at 0 and h0n; output layer at 0), [256, 384) and [384, 512)
 // the two activation buffers (layer g reads buffer g & 1 and its epilogue writes buffer (g + 1) & 1).
-template <int ACT, int CS>
+template <int ACT, int CS, bool CEMF>  // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
 __global__ void __launch_bounds__(64 + 128 * CS, 1)
 rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const long long num_tiles) {
   constexpr int kEpiThreads = 128 * CS;
@@ -158,6 +289,8 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
   //   var = exp(min + softplus(max - softplus(max - lv) - min)) = exp(min) * (1 + exp(max - min) / (1 + exp(max - lv)))
   float* c_sdmin = c_minlv;  // exp(0.5 * min_logvar)
   float* c_ratio = c_nodelta + m.D + kTileM;  // exp(max_logvar - min_logvar)
+  float* cem_tab = c_ratio + m.out;           // [2][kCemTabDims]: sampling mean, sqrt(constrained variance) (fused CEM)
+  __shared__ int sh_tail[2];
   for (int j = threadIdx.x; j < m.out; j += kThreadsAll) {
     const float mn = m.deterministic ? 0.f : m.min_lv[j], mx = m.deterministic ? 0.f : m.max_lv[j];
     c_sdmin[j] = expf(0.5f * mn);
@@ -165,6 +298,19 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     c_ratio[j] = expf(mx - mn);
   }
   for (int j = threadIdx.x; j < m.D; j += kThreadsAll) c_nodelta[j] = (!m.target_is_delta || m.no_delta[j]) ? 1.f : 0.f;
+  const int cem_dims = a.H * m.A;
+  if (CEMF && a.cem_mu) {
+    for (int d = threadIdx.x; d < cem_dims; d += kThreadsAll) {
+      const float mu = a.cem_mu[d], dp = a.cem_disp[d];
+      float sd = dp;
+      if (!a.cem_clipped) {  // trajectory_opt.py:122-125
+        const float l2 = (mu - a.cem_lb[d]) / 2.0f, u2 = (a.cem_ub[d] - mu) / 2.0f;
+        sd = sqrtf(fminf(fminf(l2 * l2, u2 * u2), dp));
+      }
+      cem_tab[d] = mu;
+      cem_tab[kCemTabDims + d] = sd;
+    }
+  }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -294,7 +440,10 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     const bool owner = cs == 0;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* my_obs = obs_s + i * p.obs_ld;
-    float* act_s1 = act_s + kTileM * p.act_ld;  // actions are double buffered by step parity
+    // three action buffers indexed by step % 3: step t+1's actions are written while step t-1's are still being scored
+    auto act_buf = [&](int tt) { return act_s + (tt % 3) * (kTileM * p.act_ld) + i * p.act_ld; };
+    const bool cem = CEMF && a.cem_mu != nullptr;
+    const bool sampler = cem && cs == (CS > 1 ? 1 : 0);  // the thread of this row that draws its sequence's actions
     uint32_t acc0_par = 0, acc1_par = 0;
     uint32_t g = 0;
     const int Kp0 = m.Kp[0];
@@ -306,7 +455,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
 
     auto build_input = [&](int tt) {
-      build_input_tmem(m, my_obs, ((tt & 1) ? act_s1 : act_s) + i * p.act_ld, c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs,
+      build_input_tmem(m, my_obs, act_buf(tt), c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs,
                        CS, bar_ar);
     };
 
@@ -328,7 +477,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
       int dead = 0;
       // reward_fn(act_t, obs_{t+1}), termination, dead mask, accumulate (model_env.py:124-129, 186-188): row owner only
       auto score = [&](int ts) {
-        const float* arow = ((ts & 1) ? act_s1 : act_s) + i * p.act_ld;
+        const float* arow = act_buf(ts);
         float rew = m.learned_rewards ? rew_s[i] : reward_eval(m.reward_fn, arow, m.A, 1, my_obs, m.D, 1);
         const bool done = term_eval(m.term_fn, my_obs, m.D, 1);
         if (valid) {
@@ -339,8 +488,10 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         dead |= done ? 1 : 0;
         tot += rew;
       };
-      const float* act_row = a.act + (rid / a.act_div) * a.act_row_stride;
-      const bool act_regs = m.A <= 8;  // next-step actions prefetched into registers (hidden behind the layers)
+      const float* act_row = cem ? nullptr : a.act + (rid / a.act_div) * a.act_row_stride;
+      const int seq_n = (int)(rid / a.P);
+      float* pop_row = (cem && a.pop_out && valid && rid % a.P == 0) ? a.pop_out + (size_t)seq_n * cem_dims : nullptr;  // in-kernel draw only
+      const bool act_regs = m.A <= 8 && !cem;  // next-step actions prefetched into registers (hidden behind the layers)
       float an[8];
       epi_bar();  // previous tile fully consumed before its row state is overwritten
       if (owner) {
@@ -354,11 +505,15 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
           tot = a.total_state[rid];
           dead = a.dead_state[rid];
         }
-        const float* ap = act_row + (long long)a.t0 * a.act_t_stride;
-        float* arow = ((a.t0 & 1) ? act_s1 : act_s) + i * p.act_ld;
+        if (!cem) {
+          const float* ap = act_row + (long long)a.t0 * a.act_t_stride;
+          float* arow = act_buf(a.t0);
 #pragma unroll 1
-        for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
+          for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
+        }
       }
+      if (CEMF && sampler) cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, seq_n, a.t0, m.A,
+                                      act_buf(a.t0), pop_row);
       epi_bar();
       build_input(a.t0);
 
@@ -367,7 +522,7 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         int sp = 0;
         if (stamp) a.timeline[sp++] = clock64();  // 0: step start (layer-0 operand already handed over)
         const bool more = t + 1 < a.t1;
-        if (owner && act_regs && more) {  // global loads complete under the layers
+        if (owner && act_regs && more) {  // global loads complete under the layers (not in fused-CEM mode)
           const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
 #pragma unroll
           for (int j = 0; j < 8; ++j) an[j] = (valid && j < m.A) ? ap[j] : 0.f;
@@ -436,10 +591,14 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
             }
             // previous step's reward / termination, off the critical path (the owner has no noise group in this gap)
             if (l == 1 && owner && t > a.t0 && defer_score) score(t - 1);
-          } else if (l == 2 && owner) {
+            // fused CEM: next step's actions are drawn here by the row's sampler thread (third action buffer)
+            if (CEMF && l == (L > 1 ? 1 : 0) && sampler && more)
+              cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, seq_n, t + 1,
+                                 m.A, act_buf(t + 1), pop_row);
+          } else if (l == 2 && owner && !cem) {
             if (!more) continue;
             // next step's actions -> the other action buffer (the one score(t - 1) just finished reading)
-            float* arow = (((t + 1) & 1) ? act_s1 : act_s) + i * p.act_ld;
+            float* arow = act_buf(t + 1);
             if (act_regs) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -451,8 +610,8 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
             }
           }
         }
-        if (L < 3 && owner && more) {  // shallow models: the action hand-over did not fit in a gap above
-          float* arow = (((t + 1) & 1) ? act_s1 : act_s) + i * p.act_ld;
+        if (L < 3 && owner && more && !cem) {  // shallow models: the action hand-over did not fit in a gap above
+          float* arow = act_buf(t + 1);
           const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
   #pragma unroll 1
         for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
@@ -536,6 +695,27 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  // ---- fused CEM iteration: the last CTA to get here refits the sampling distribution ----
+  if (CEMF && a.tail_counter) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      sh_tail[0] = atomicAdd(a.tail_counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_tail[0]) {
+      __threadfence();
+      TailArgs* ta = reinterpret_cast<TailArgs*>(ring);  // the weight ring is idle now: argument block + scratch
+      if (threadIdx.x == 0) {
+        ta->N = a.N; ta->P = a.P; ta->tail_elite_num = a.tail_elite_num; ta->cem_clipped = a.cem_clipped;
+        ta->tail_alpha = a.tail_alpha; ta->total_state = a.total_state; ta->pop_out = a.pop_out;
+        ta->tail_values = a.tail_values; ta->tail_mu = a.tail_mu; ta->tail_disp = a.tail_disp;
+        ta->tail_best_value = a.tail_best_value; ta->tail_best_solution = a.tail_best_solution;
+        ta->tail_counter = a.tail_counter;
+      }
+      __syncthreads();
+      cem_tail_refit(ta, cem_dims, ring + 256, &sh_tail[1]);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -781,8 +961,8 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   uint32_t off = 0;
   p.off_A = 0;
   p.off_obs = off; off += (uint32_t)kTileM * p.obs_ld * 4;
-  p.off_act = off; off += 2u * (uint32_t)kTileM * p.act_ld * 4;
-  p.off_const = off; off += (uint32_t)(2 * m.in + 3 * m.out + m.D + kTileM) * 4;
+  p.off_act = off; off += 3u * (uint32_t)kTileM * p.act_ld * 4;
+  p.off_const = off; off += (uint32_t)(2 * m.in + 3 * m.out + m.D + kTileM + 2 * kCemTabDims) * 4;
   off = (off + 15u) & ~15u;
   p.off_bar = off; off += (2 * kMaxStages + 4) * 8 + 16;
   off = (off + 127u) & ~127u;
@@ -818,11 +998,19 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
     tiles = (long long)m.M * ((Bm + kTileM - 1) / kTileM);
   }
   const unsigned grid = (unsigned)min((long long)g_sm_count, tiles);
+  const bool cemf = a.cem_mu != nullptr || a.tail_counter != nullptr;
   void (*kern)(const ModelDev, const RolloutArgs, const TcPlan, const long long) = nullptr;
   switch (m.act) {
-    case B200PETS_ACT_SILU: kern = rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit>; break;
-    case B200PETS_ACT_RELU: kern = rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit>; break;
-    default: kern = rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit>; break;
+    case B200PETS_ACT_SILU:
+      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, true> : rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, false>;
+      break;
+    case B200PETS_ACT_RELU:
+      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, true> : rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, false>;
+      break;
+    default:
+      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, true>
+                  : rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, false>;
+      break;
   }
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
   kern<<<grid, 64 + 128 * kEpiSplit, p.smem_bytes, stream>>>(m, a, p, tiles);

@@ -305,6 +305,36 @@ def test_fused_cem_plan_matches_reference(golden_dir, precision, tol):
         assert np.abs(sol.cpu().numpy() - g["solution"]).max() <= 0.1  # elite membership may flip at bf16
 
 
+def test_fused_iteration_kernel_equals_multi_kernel_plan():
+    """One kernel per CEM iteration (in-kernel sampling + rollout + last-CTA refit) against the
+    sample -> rollout -> particle-mean -> refit kernel sequence: same Philox keys => same population and returns."""
+    import mbrl_lib_b200 as bp
+    from mbrl_lib_b200.planning import _FusedObjective
+
+    spec = syn.CASES["halfcheetah"]
+    H, A = spec.horizon, spec.act_dim
+    lb, ub = np.full((H, A), spec.action_lb).tolist(), np.full((H, A), spec.action_ub).tolist()
+    inp = syn.make_rollout_inputs(spec, with_noise=False)
+    out = {}
+    for fused in ("1", "0", "sik"):
+        os.environ["B200PETS_CEM_FUSED"] = "0" if fused == "0" else "1"
+        os.environ["B200PETS_CEM_SAMPLE_IN_KERNEL"] = "1" if fused == "sik" else "0"
+        _, _, env = make_env("halfcheetah", "bf16_tc", ts1="tile_shuffle")
+        opt = bp.CEMOptimizer(3, 0.1, spec.population, lb, ub, 0.1, DEV, return_mean_elites=True)
+        opt.record_values = True
+        sol = opt.optimize(_FusedObjective(env, inp["obs0"], spec.particles), x0=torch.zeros(H, A, device=DEV))
+        torch.cuda.synchronize()
+        out[fused] = (sol.cpu().numpy(), opt.last_values.cpu().numpy())
+    os.environ.pop("B200PETS_CEM_FUSED")
+    os.environ.pop("B200PETS_CEM_SAMPLE_IN_KERNEL")
+    assert np.array_equal(out["sik"][1][0], out["0"][1][0])  # population drawn inside the rollout kernel: same keys
+    np.testing.assert_allclose(out["sik"][0], out["0"][0], rtol=0, atol=1e-4)
+    assert np.array_equal(out["1"][1][0], out["0"][1][0])  # iteration 0: identical population, identical returns
+    np.testing.assert_allclose(out["1"][1], out["0"][1], rtol=0, atol=5e-3)  # later iterations: refit summation order
+    np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=0, atol=1e-4)
+    assert np.isfinite(out["1"][0]).all()
+
+
 # ---- in-kernel RNG: distribution-level checks ------------------------------------------------------------
 def test_truncated_normal_sampler_statistics():
     import mbrl_lib_b200 as bp
