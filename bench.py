@@ -33,6 +33,7 @@ WORKLOAD = "halfcheetah"  # BASELINE.json configs[1]
 CEM_ITERS, ELITE_RATIO, ALPHA = 5, 0.1, 0.1
 FLOP_PER_SEQ = 157.68e6  # 2 * sum K*N (true dims) * P * H = 262 800 * 20 * 30
 METRIC = "candidate action-sequences/sec, PETS HalfCheetah CEM"
+NCU_DRAM_BYTES_PER_LAUNCH = 1936896 + 188416  # measured once per change with ncu (see profiles/), not at bench time
 
 
 def measured_peak_tflops():
@@ -247,7 +248,9 @@ def run_ours(args):
                        "precision": env.precision},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "rollout_tc_kernel (one CEM iteration: 500 sequences x 20 particles x 30 steps)",
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one "
+                         "launch (profiles/r1_rollout_tc_final_ncu_full_summary.csv): 1.94 MB + 0.19 MB; algorithmic: 1.3 MB bf16 weights + "
+                         "0.36 MB actions + 2 KB returns", "kernel": "rollout_tc_kernel (one CEM iteration: 500 sequences x 20 particles x 30 steps)",
                          "kernel_ms": kern_ms_avg, "peak_source": peak_src,
                          "algorithmic_flop_per_launch": N * FLOP_PER_SEQ},
             "clocks": clocks,
