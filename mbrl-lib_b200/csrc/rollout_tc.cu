@@ -1,13 +1,16 @@
 // Tensor-core rollout of the ensemble MLP on sm_100a: bf16 operands, fp32 accumulation in TMEM.
 //
-// One persistent CTA per SM walks 128-row tiles through steps [t0, t1) of the horizon without leaving the
-// chip: the row state (observation, return, dead flag) stays in shared memory / registers, each layer is a
-// chain of tcgen05.mma (M=128, N=padded layer width, K=16) whose A operand (activations) is written by the
-// epilogue warps straight into the UMMA canonical shared-memory layout and whose B operand (weights) is
-// streamed from the L2-resident packed image through a ring of 1-D TMA bulk copies.
+// One persistent CTA per SM walks 128-row tiles through steps [t0, t1) of the horizon without leaving the chip:
+//  * row state (observation, return, dead flag, actions) stays in shared memory / registers;
+//  * each layer is a chain of tcgen05.mma (M=128, K=16) in the A-from-TMEM form: the activations are written by the
+//    epilogue warps as bf16 pairs with tcgen05.st into a TMEM buffer and never touch shared memory;
+//  * the B operand (weights) is streamed from the L2-resident packed image into two shared-memory layer slots by
+//    1-D TMA bulk copies (cp.async.bulk + mbarrier expect_tx), one slot in use while the next layer is in flight;
+//  * hidden layers are split in two N halves so that epilogue, MMAs of the other half and the next layer's first
+//    K steps overlap (see the kernel's header comment).
 //
-// Warp roles (64 + 128 * CS threads):  warp 0 = weight producer (cp.async.bulk + mbarrier),
-//                            warp 1 = TMEM allocator + MMA issuer (single thread),
+// Warp roles (64 + 128 * CS threads):  warp 0 = weight producer (one elected lane),
+//                            warp 1 = TMEM allocator + MMA issuer (converged warp, MMAs under elect.sync),
 //                            warps 2.. = 4 * CS epilogue warps: warp (q, cs) <-> TMEM lanes 32q..32q+31 (tile rows)
 //                            and every CS-th 16-column chunk; thread (row, cs == 0) owns the row's scalar state.
 //
@@ -446,7 +449,6 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     const bool sampler = cem && cs == (CS > 1 ? 1 : 0);  // the thread of this row that draws its sequence's actions
     uint32_t acc0_par = 0, acc1_par = 0;
     uint32_t g = 0;
-    const int Kp0 = m.Kp[0];
     const int ngroups = (m.out + 3) >> 2;
     const bool draw = !m.deterministic && a.sample;
     // scoring of step t may be deferred into the gap after hidden layer 2 of step t + 1 only if another hidden layer
