@@ -970,7 +970,7 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   off = (off + 127u) & ~127u;
   p.off_ring = off;
   int S = ((int)max_smem - (int)off) / (int)p.stage_bytes;
-  if (S < 2) return false;  // one layer in use, the next one in flight
+  if (S < 1) return false;  // S >= 2: one layer in use, the next one in flight; S == 1 (wide layers): no prefetch
   p.nstages = min(S, kMaxStages);
   p.smem_bytes = off + (uint32_t)p.nstages * p.stage_bytes;
   *out = p;

@@ -100,6 +100,14 @@ _register(CaseSpec("mbpo_halfcheetah", obs_dim=17, act_dim=6, learned_rewards=Tr
                    population=100000, horizon=1, particles=1))
 _register(CaseSpec("mbpo_halfcheetah_small", obs_dim=17, act_dim=6, learned_rewards=True, reward_fn=None,
                    population=1000, horizon=1, particles=1))
+# tensor-core plan edge cases: hid % 16 == 0 (bias columns spill into an extra K step), wide output layer that cannot
+# start under the last hidden epilogue (2 * round16(out) > first N half), large input (8 K steps)
+_register(CaseSpec("tc_hid64", obs_dim=9, act_dim=2, hid_size=64, num_layers=3, ensemble_size=3, elites=None,
+                   activation="silu", propagation="random_model", normalize="float32", learned_rewards=True, reward_fn=None,
+                   term_fn="no_termination", population=48, horizon=6, particles=4))
+_register(CaseSpec("tc_wide", obs_dim=100, act_dim=20, hid_size=240, num_layers=2, ensemble_size=2, elites=None,
+                   activation="relu", propagation="fixed_model", normalize="float64", learned_rewards=True, reward_fn=None,
+                   term_fn="humanoid", population=40, horizon=5, particles=4, obs0_first=1.4))
 # coverage cases: relu + expectation / deterministic / cartpole_pets preprocess / hopper termination
 _register(CaseSpec("relu_expectation", obs_dim=11, act_dim=3, hid_size=64, num_layers=2, ensemble_size=3,
                    elites=None, activation="relu", propagation="expectation", normalize=None,
