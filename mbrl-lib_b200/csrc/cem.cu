@@ -200,7 +200,10 @@ struct SelArgs {
   float* partial;  // [32][dims] scratch
 };
 
-__global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArgs s) {
+__global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArgs s_in) {
+  extern __shared__ float sel_dyn_smem[];  // [33][dims] partial sums when they fit, else the global workspace is used
+  SelArgs s = s_in;
+  if (s.partial == nullptr) s.partial = sel_dyn_smem;
   __shared__ int hist[256];
   __shared__ int warp_sums[32];
   __shared__ int sh_total;
@@ -529,7 +532,17 @@ static int run_select(int mode, int n, int dims, int k, float alpha, int unbiase
   s.best_value = best_value; s.best_solution = best_solution; s.elites_out = elites_out; s.records = records;
   s.partial = reinterpret_cast<float*>(workspace);
   s.elite_idx = elite_idx ? elite_idx : reinterpret_cast<int*>(reinterpret_cast<float*>(workspace) + 33 * (size_t)dims);
-  cem_select_kernel<<<1, kSelThreads, 0, (cudaStream_t)stream>>>(s);
+  size_t dyn = 0;
+  if ((size_t)33 * dims * sizeof(float) <= 160 * 1024) {  // partial sums in shared memory (latency-bound reduction)
+    dyn = (size_t)33 * dims * sizeof(float);
+    s.partial = nullptr;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(cem_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+  }
+  cem_select_kernel<<<1, kSelThreads, dyn, (cudaStream_t)stream>>>(s);
   CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }
