@@ -11,6 +11,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    try:  # the oracle's small GEMMs are far slower with one thread per hardware thread on a 128-thread host
+        import torch
+
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+    except Exception:  # pragma: no cover
+        pass
 
 
 def pytest_collection_modifyitems(config, items):
