@@ -9,7 +9,8 @@ population 500 candidate sequences, each rolled out for H = 30 steps with 20 par
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 N > 1 (under torchrun): weak scaling -- every rank plans over its own 500-sequence shard of a 500 x N
-population, ONE all-gather of local top-k records per CEM iteration (mbrl_lib_b200.dist).
+population, ONE all-gather of local top-k records per CEM iteration (mbrl_lib_b200.dist); ``e2e`` is then
+``ShardedCEMOptimizer.optimize`` per call with the host observation in and the host plan out, max over ranks.
 ``--impl reference``: the oracle port of the reference's PyTorch path timed on the host CPUs (rank 0 only).
 """
 import argparse
