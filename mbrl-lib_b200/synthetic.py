@@ -105,6 +105,9 @@ _register(CaseSpec("mbpo_halfcheetah_small", obs_dim=17, act_dim=6, learned_rewa
 _register(CaseSpec("tc_hid64", obs_dim=9, act_dim=2, hid_size=64, num_layers=3, ensemble_size=3, elites=None,
                    activation="silu", propagation="random_model", normalize="float32", learned_rewards=True, reward_fn=None,
                    term_fn="no_termination", population=48, horizon=6, particles=4))
+_register(CaseSpec("tc_shallow", obs_dim=6, act_dim=2, hid_size=32, num_layers=1, ensemble_size=4, elites=(2, 0),
+                   activation="leaky_relu", propagation="random_model", normalize=None, reward_fn="halfcheetah",
+                   term_fn="no_termination", population=33, horizon=9, particles=4))
 _register(CaseSpec("tc_wide", obs_dim=100, act_dim=20, hid_size=240, num_layers=2, ensemble_size=2, elites=None,
                    activation="relu", propagation="fixed_model", normalize="float64", learned_rewards=True, reward_fn=None,
                    term_fn="humanoid", population=40, horizon=5, particles=4, obs0_first=1.4))
