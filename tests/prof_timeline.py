@@ -22,4 +22,4 @@ print("epilogue thread stamps (cycles since step start):", [x - t0 for x in b[:2
 print("fine stamps:", [x - t0 for x in b[40:56] if x])
 for l in range(5):
     s = b[64 + 4 * l: 68 + 4 * l]
-    print(f"mma layer {l}: wait_a_start {s[0]-t0}, a_ready {s[1]-t0}, last_stage_full {s[2]-t0}, issued {s[3]-t0}")
+    print(f"mma layer {l}: starts waiting {s[0]-t0}, weights + first activation half ready {s[1]-t0}, all MMAs issued {s[3]-t0}")
