@@ -440,7 +440,9 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     const int q = warp & 3;            // TMEM lane quadrant this warp may access (hardware: warp id % 4)
     const int cs = (warp - 2) >> 2;    // column split
     const int i = q * 32 + lane;       // tile row
-    const bool owner = cs == 0;
+    const bool owner = cs == 0;                     // loads the row's observation / actions
+    const bool scorer = cs == (CS >= 3 ? 2 : 0);    // owns return / dead flag: scores reward + termination (a thread
+                                                    // with an idle gap after layer 1, not the action-loading one)
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* my_obs = obs_s + i * p.obs_ld;
     // three action buffers indexed by step % 3: step t+1's actions are written while step t-1's are still being scored
@@ -496,16 +498,16 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
       const bool act_regs = m.A <= 8 && !cem;  // next-step actions prefetched into registers (hidden behind the layers)
       float an[8];
       epi_bar();  // previous tile fully consumed before its row state is overwritten
+      if (scorer && a.load_state && valid) {
+        tot = a.total_state[rid];
+        dead = a.dead_state[rid];
+      }
       if (owner) {
 #pragma unroll 1
         for (int d = 0; d < m.D; ++d) {
           float v = 0.f;
           if (valid) v = a.init_from_obs0 ? a.obs0[d] : a.obs_in[rid * m.D + d];
           my_obs[d] = v;
-        }
-        if (a.load_state && valid) {
-          tot = a.total_state[rid];
-          dead = a.dead_state[rid];
         }
         if (!cem) {
           const float* ap = act_row + (long long)a.t0 * a.act_t_stride;
@@ -591,8 +593,8 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
 #pragma unroll
               for (int e = 0; e < 4; ++e) zpre[l & 1][e] = z4[e];
             }
-            // previous step's reward / termination, off the critical path (the owner has no noise group in this gap)
-            if (l == 1 && owner && t > a.t0 && defer_score) score(t - 1);
+            // previous step's reward / termination, off the critical path (the scorer thread has no noise group here)
+            if (l == 1 && scorer && t > a.t0 && defer_score) score(t - 1);
             // fused CEM: next step's actions are drawn here by the row's sampler thread (third action buffer)
             if (CEMF && l == (L > 1 ? 1 : 0) && sampler && more)
               cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, seq_n, t + 1,
@@ -680,14 +682,15 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         if (more) build_input(t + 1);             // next step's layer 0 starts while the owner scores this step
         if (stamp) a.timeline[sp++] = clock64();  // next input handed over
         // ---- reward, termination, accumulate: deferred into a gap of the next step when the model is deep enough ----
-        if (owner && !(more && defer_score)) score(t);
+        if (scorer && !(more && defer_score)) score(t);
         if (stamp) a.timeline[sp++] = clock64();  // reward done
       }
       // ---- store row state ----
-      if (owner && a.store_state && valid) {
-        if (a.obs_out)
+      if (owner && a.store_state && valid && a.obs_out) {
 #pragma unroll 1
-          for (int d = 0; d < m.D; ++d) a.obs_out[rid * m.D + d] = my_obs[d];
+        for (int d = 0; d < m.D; ++d) a.obs_out[rid * m.D + d] = my_obs[d];
+      }
+      if (scorer && a.store_state && valid) {
         if (a.total_state) a.total_state[rid] = tot;
         if (a.dead_state) a.dead_state[rid] = (uint8_t)dead;
       }
