@@ -44,7 +44,7 @@ def _worker(rank, world, port, out):
 
 def test_sharded_cem_record_exchange_world2():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert all(out[r] for r in range(world)), dict(out)
