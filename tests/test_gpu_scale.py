@@ -119,3 +119,52 @@ def test_icem_over_model_runs_and_improves():
     assert max(best[1:]) >= best[0] - 0.05  # later generations are at least as good as the first (noisy objective)
     sol2 = opt.optimize(obj, x0=torch.zeros(H, A, device=DEV))  # second call: shifted elites of the previous plan
     assert bool(torch.isfinite(sol2).all())
+
+
+def _line_world(device):
+    """A hand-built deterministic 'ensemble' that is exactly a 1-D point mass (ReLU pairs encode identity / abs):
+    next_pos = pos + 0.1 * a, learned reward = -|next_pos|.  Plays the role of the reference's MockLineEnv
+    integration test (tests/algorithms/test_algorithms.py:44-68) without needing model training."""
+    import mbrl_lib_b200 as bp
+
+    mlp = bp.GaussianMLP(2, 2, device, num_layers=1, ensemble_size=2, hid_size=32, deterministic=True,
+                         propagation_method="random_model", activation="relu")
+    w0 = torch.zeros(2, 2, 32)
+    w0[:, 1, 0], w0[:, 1, 1] = 1.0, -1.0                      # relu(a), relu(-a)
+    w0[:, 0, 2], w0[:, 1, 2] = 1.0, 0.1                       # relu(pos + 0.1 a)
+    w0[:, 0, 3], w0[:, 1, 3] = -1.0, -0.1                     # relu(-(pos + 0.1 a))
+    w1 = torch.zeros(2, 32, 2)
+    w1[:, 0, 0], w1[:, 1, 0] = 0.1, -0.1                      # delta = 0.1 a
+    w1[:, 2, 1], w1[:, 3, 1] = -1.0, -1.0                     # reward = -|pos + 0.1 a|
+    with torch.no_grad():
+        mlp.hidden_layers[0][0].weight.copy_(w0)
+        mlp.hidden_layers[0][0].bias.zero_()
+        mlp.mean_and_logvar.weight.copy_(w1)
+        mlp.mean_and_logvar.bias.zero_()
+    return bp.OneDTransitionRewardModel(mlp, target_is_delta=True, normalize=False, learned_rewards=True)
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16_tc"])
+def test_closed_loop_mpc_reaches_goal(precision):
+    """Behavioural check of the whole agent loop on the GPU (act -> fused CEM plan -> warm-start shift -> act ...)."""
+    import mbrl_lib_b200 as bp
+    from mbrl_lib_b200 import functions
+    from test_gpu_parity import _Env
+
+    class _Spec:
+        obs_dim, act_dim, action_lb, action_ub = 1, 1, -1.0, 1.0
+
+    model = _line_world(DEV)
+    env = bp.ModelEnv(_Env(_Spec), model, functions.no_termination, None, generator=torch.Generator(device=DEV),
+                      precision=precision, ts1="tile_shuffle")
+    cfg = {"_target_": "mbrl.planning.TrajectoryOptimizerAgent", "planning_horizon": 5, "replan_freq": 1,
+           "optimizer_cfg": {"_target_": "mbrl.planning.CEMOptimizer", "num_iterations": 4, "elite_ratio": 0.1,
+                             "population_size": 256, "alpha": 0.1, "device": DEV, "return_mean_elites": True}}
+    agent = bp.create_trajectory_optim_agent_for_model(env, cfg, num_particles=2)
+    pos, total = 1.0, 0.0
+    for _ in range(18):
+        a = float(np.clip(agent.act(np.array([pos])), -1, 1)[0])
+        pos = pos + 0.1 * a  # the true environment is the same point mass
+        total += -abs(pos)
+    assert abs(pos) < 0.12, pos            # started at 1.0, can move 0.1 per step
+    assert total > -7.5, total             # an agent that never moves collects -18
