@@ -67,8 +67,12 @@ class ModelEnv:
         if self._obs_pin is None or self._obs_pin.numel() != D:
             self._obs_pin = torch.empty(D, dtype=torch.float32).pin_memory()
             self._obs_dev = torch.empty(D, dtype=torch.float32, device=self.device)
+            self._obs_evt = torch.cuda.Event()
+        else:
+            self._obs_evt.synchronize()  # the previous async H2D copy must have read the pinned buffer before we overwrite it
         self._obs_pin.copy_(torch.from_numpy(np.ascontiguousarray(initial_state, dtype=np.float32)))
         self._obs_dev.copy_(self._obs_pin, non_blocking=True)
+        self._obs_evt.record()
         return self._obs_dev
 
     # ---- reference API ---------------------------------------------------------------------------------
