@@ -146,7 +146,8 @@ int b200pets_eval_sequences(b200pets_model_t model, const b200pets_rollout_cfg* 
                             float* row_returns, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ModelEnv.step (mbrl/models/model_env.py:87-140) for a batch of B independent states.
- *   perm [dev] int64[B] or NULL (TS1: tile shuffle; TSinf: identity = propagation_indices given by caller)
+ *   perm [dev] int64[B]; NULL is allowed for TS1 (tile shuffle) and expectation; TSinf requires the caller's
+ *        propagation_indices and returns B200PETS_EINVAL without them (gaussian_mlp.py:208-211)
  *   eps  [dev] float[B][out] or NULL; sample == 0 returns the mean prediction (deterministic=True). */
 int b200pets_step(b200pets_model_t model, int32_t precision, int32_t propagation, int64_t batch,
                   const float* obs, const float* act, const int64_t* perm, const float* eps, uint64_t seed,

@@ -9,7 +9,7 @@ _LAZY = {
     "ModelEnv": "model_env", "StagedModel": "staging",
     "Agent": "planning", "Optimizer": "planning", "CEMOptimizer": "planning", "ICEMOptimizer": "planning", "MPPIOptimizer": "planning",
     "TrajectoryOptimizer": "planning", "TrajectoryOptimizerAgent": "planning",
-    "create_trajectory_optim_agent_for_model": "planning", "complete_agent_cfg": "planning",
+    "create_trajectory_optim_agent_for_model": "planning", "complete_agent_cfg": "planning", "rollout_model_env": "planning",
     "GaussianMLP": "models", "OneDTransitionRewardModel": "models", "EnsembleLinearLayer": "models",
     "Normalizer": "models", "model_from_arrays": "models",
 }

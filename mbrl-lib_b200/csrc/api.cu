@@ -253,7 +253,7 @@ int b200pets_model_create(const b200pets_model_desc* desc, const float* const* w
 int b200pets_model_refresh(b200pets_model_t model, const float* const* weights, const float* const* biases,
                            const int32_t* members, const double* norm_mean, const double* norm_std,
                            const float* min_logvar, const float* max_logvar, void* stream) {
-  if (!model) return b200pets_set_error(B200PETS_EINVAL, "model_refresh: null model");
+  if (!model || !weights || !biases || !members) return b200pets_set_error(B200PETS_EINVAL, "model_refresh: null argument");
   for (int i = 0; i < model->desc.num_members; ++i)
     if (members[i] < 0 || members[i] >= model->desc.ensemble_size) return b200pets_set_error(B200PETS_EINVAL, "model_refresh: member index out of range");
   return stage_model(model, weights, biases, members, norm_mean, norm_std, min_logvar, max_logvar, nullptr, 0, false,
@@ -361,12 +361,11 @@ int b200pets_step(b200pets_model_t model, int32_t precision, int32_t propagation
   if (!model || !obs || !act || !next_obs) return b200pets_set_error(B200PETS_EINVAL, "step: null argument");
   const b200pets_model_desc& d = model->desc;
   if (batch <= 0) return b200pets_set_error(B200PETS_EINVAL, "step: empty batch");
-  if (propagation != B200PETS_PROP_EXPECTATION && batch % d.num_members != 0)
+  if (batch % d.num_members != 0)  // mbrl/models/gaussian_mlp.py:195-200 (checked for every propagation method)
     return b200pets_set_error(B200PETS_EINVAL, "GaussianMLP ensemble requires batch size to be a multiple of the number of models. "
                                                "Current batch size is %lld for %d models.", (long long)batch, d.num_members);
-  if (propagation == B200PETS_PROP_EXPECTATION && batch % d.num_members != 0)
-    return b200pets_set_error(B200PETS_EINVAL, "GaussianMLP ensemble requires batch size to be a multiple of the number of models. "
-                                               "Current batch size is %lld for %d models.", (long long)batch, d.num_members);
+  if (propagation == B200PETS_PROP_FIXED_MODEL && !perm)  // gaussian_mlp.py:208-211
+    return b200pets_set_error(B200PETS_EINVAL, "When using propagation='fixed_model', `propagation_indices` must be provided.");
   RolloutArgs a{};
   a.N = (int)batch; a.H = 1; a.P = 1; a.B = batch;
   a.t0 = 0; a.t1 = 1;

@@ -17,7 +17,7 @@ import abc
 import ctypes as C
 import importlib
 import time
-from typing import Callable, List, Optional, Sequence
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -459,3 +459,23 @@ def create_trajectory_optim_agent_for_model(model_env, agent_cfg, num_particles:
     agent = _instantiate(agent_cfg)
     agent.set_model_env(model_env, num_particles)
     return agent
+
+
+def rollout_model_env(model_env, initial_obs: np.ndarray, plan: Optional[np.ndarray] = None, agent: Optional[Agent] = None,
+                      num_samples: int = 1) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Execute ``plan`` (or ``agent.plan``'s, which takes precedence) open loop on the model, ``num_samples`` copies of
+    ``initial_obs`` side by side, predictions taken with ``sample=False`` (mbrl/util/common.py:416-454).
+
+    Returns ``(observations [len+1, num_samples, D], rewards [len, num_samples, 1], plan)``.  One ``b200pets_step``
+    launch per action; the per-step numpy hand-over is the reference's interface for this diagnostic.
+    """
+    if agent:
+        plan = agent.plan(initial_obs[None, :])
+    start = np.tile(initial_obs, (num_samples, 1))
+    model_state = model_env.reset(start, return_as_np=True)
+    observations, rewards = [start], []
+    for action in plan:
+        next_obs, reward, _, model_state = model_env.step(np.tile(action, (num_samples, 1)), model_state, sample=False)
+        observations.append(next_obs)
+        rewards.append(reward)
+    return np.stack(observations), np.stack(rewards), plan

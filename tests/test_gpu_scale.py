@@ -168,3 +168,29 @@ def test_closed_loop_mpc_reaches_goal(precision):
         total += -abs(pos)
     assert abs(pos) < 0.12, pos            # started at 1.0, can move 0.1 per step
     assert total > -7.5, total             # an agent that never moves collects -18
+
+
+@pytest.mark.gpu
+def test_rollout_model_env_matches_oracle_open_loop():
+    """util/common.py:416-454 on the CUDA step kernel vs. the oracle stepping the same plan (TSinf, sample=False)."""
+    import mbrl_lib_b200 as bp
+    from oracle import pets_oracle as po
+    from tests.test_gpu_parity import make_env
+
+    spec, arrays, env = make_env("hopper_tsinf", "f32")
+    S, L = 3 * spec.num_models, 6
+    rng = np.random.default_rng(5)
+    obs0 = rng.standard_normal(spec.obs_dim).astype(np.float32)
+    plan = rng.uniform(spec.action_lb, spec.action_ub, size=(L, spec.act_dim)).astype(np.float32)
+    torch.manual_seed(11)
+    obs, rew, got_plan = bp.rollout_model_env(env, obs0, plan, None, num_samples=S)
+    assert obs.shape == (L + 1, S, spec.obs_dim) and rew.shape == (L, S, 1) and got_plan is plan
+    torch.manual_seed(11)
+    perm = torch.randperm(S, device="cuda").cpu()  # the draw ModelEnv.reset made
+    m = po.OracleModel(spec, arrays)
+    o = torch.from_numpy(np.tile(obs0, (S, 1)))
+    for t in range(L):
+        o, r, _ = m.step(o, torch.from_numpy(np.tile(plan[t], (S, 1))), perm, None, sample=False)
+        scale = max(1.0, float(o.abs().max()))
+        assert np.abs(obs[t + 1] - o.numpy()).max() <= 5e-4 * scale
+        assert np.abs(rew[t] - r.numpy().reshape(S, 1)).max() <= 5e-4 * max(1.0, float(r.abs().max()))

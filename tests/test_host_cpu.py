@@ -158,3 +158,34 @@ def test_staging_reads_the_real_reference_objects():
         assert functions.resolve_reward(getattr(R, name)) == _lib.REWARD[name]
     for name in ("hopper", "cartpole", "inverted_pendulum", "walker2d", "ant", "humanoid"):
         assert functions.resolve_term(getattr(T, name)) == _lib.TERM[name]
+
+
+def test_rollout_model_env_protocol():
+    """Same protocol the reference checks in tests/core/test_common_utils.py:195-227, with stand-in env / agent."""
+    from mbrl_lib_b200.planning import rollout_model_env
+
+    class _CountingEnv:
+        def reset(self, obs0, return_as_np=None):
+            self.obs, self.kw = obs0, return_as_np
+            return {}
+
+        def step(self, action, model_state, sample=None):
+            assert sample is False
+            self.obs = self.obs + action[:, :1]
+            n = self.obs.shape[0]
+            return self.obs, np.ones(n), np.zeros(n), {}
+
+    class _FixedAgent:
+        def __init__(self, n):
+            self.seq = np.ones((n, 1))
+
+        def plan(self, obs):
+            assert obs.ndim == 2  # the reference hands the agent a [1, D] observation
+            return self.seq
+
+    env, agent, D, L, S = _CountingEnv(), _FixedAgent(12), 7, 12, 3
+    obs, rew, plan = rollout_model_env(env, np.zeros(D), 0 * agent.seq, agent, num_samples=S)  # agent wins over plan
+    assert env.kw is True and obs.shape == (L + 1, S, D) and rew.shape == (L, S) and plan.shape == (L, 1)
+    assert [o.min() for o in obs] == list(range(L + 1))
+    obs, _, _ = rollout_model_env(env, np.zeros(D), 3 * agent.seq, None, num_samples=S)
+    assert [o.max() for o in obs] == [3 * i for i in range(L + 1)]
