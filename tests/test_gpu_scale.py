@@ -175,7 +175,6 @@ def test_rollout_model_env_matches_oracle_open_loop():
     """util/common.py:416-454 on the CUDA step kernel vs. the oracle stepping the same plan (TSinf, sample=False)."""
     import mbrl_lib_b200 as bp
     from oracle import pets_oracle as po
-    from tests.test_gpu_parity import make_env
 
     spec, arrays, env = make_env("hopper_tsinf", "f32")
     S, L = 3 * spec.num_models, 6
