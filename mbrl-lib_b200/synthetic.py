@@ -236,3 +236,22 @@ def make_cem_noise(spec: CaseSpec, iters: int, seed: int = 4321) -> Dict[str, np
     eps = g.standard_normal((iters, H, B, spec.out_size), dtype=np.float32)
     perms = np.stack([[g.permutation(B) for _ in range(H)] for _ in range(iters)]).astype(np.int64)
     return {"z": z, "eps": eps, "perms": perms}
+
+
+def counter_world(hid_size: int = 32):
+    """A hand-built deterministic ReLU ensemble that IS the reference's known-answer model
+    (tests/core/test_models.py:337-385): next_obs = obs + a, reward = next_obs, exact in fp32 and in bf16 for the
+    small integers involved, so ``evaluate_action_sequences`` must return exactly H(H+1)/2 * a from obs0 = 0, a > 0.
+    """
+    spec = CaseSpec("counter_world", obs_dim=1, act_dim=1, hid_size=hid_size, num_layers=1, ensemble_size=2, elites=None,
+                    activation="relu", propagation="random_model", normalize=None, learned_rewards=True,
+                    reward_fn=None, deterministic=True, population=4, horizon=9, particles=9, action_lb=0.0, action_ub=2.0)
+    w0 = np.zeros((2, 2, hid_size), np.float32)
+    w0[:, 1, 0] = 1.0                   # h0 = relu(a)
+    w0[:, 0, 1] = w0[:, 1, 1] = 1.0     # h1 = relu(obs + a)
+    w1 = np.zeros((2, hid_size, 2), np.float32)
+    w1[:, 0, 0] = 1.0                   # delta  = a
+    w1[:, 1, 1] = 1.0                   # reward = obs + a
+    arrays = {"weights": [w0, w1], "biases": [np.zeros((2, 1, hid_size), np.float32), np.zeros((2, 1, 2), np.float32)],
+              "min_logvar": np.full((1, 2), -10.0, np.float32), "max_logvar": np.full((1, 2), 0.5, np.float32)}
+    return spec, arrays

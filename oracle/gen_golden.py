@@ -284,6 +284,23 @@ def gen_cem_model():
     print("cem_model", sol[0].tolist())
 
 
+def gen_counter_world():
+    """The reference's closed-form case (tests/core/test_models.py:365-385) run through the REAL GaussianMLP path
+    with the hand-built ReLU ensemble of synthetic.counter_world: returns must be H(H+1)/2 * a exactly."""
+    spec, arrays = syn.counter_world()
+    env = build_reference(spec, arrays)
+    N = 4
+    grid = np.zeros((9, 9, 2), np.float32)
+    for P in range(1, 10):
+        for H in range(1, 10):
+            for ai, a in enumerate((1.0, 2.0)):
+                ret = env.evaluate_action_sequences(torch.full((N, H, 1), a), np.zeros(1), P)
+                assert torch.equal(ret, torch.full((N,), H * (H + 1) / 2 * a)), (P, H, a, ret)
+                grid[P - 1, H - 1, ai] = ret[0].item()
+    np.savez(os.path.join(GOLD, "kat_counter_world.npz"), returns=grid, model_sum=syn.checksum(arrays))
+    print("counter_world", grid[8, 8].tolist())
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
@@ -298,3 +315,4 @@ if __name__ == "__main__":
     gen_icem()
     gen_mppi()
     gen_cem_model()
+    gen_counter_world()

@@ -436,3 +436,28 @@ def test_cem_improves_objective_rosenbrock():
     # the reference's CEM (oracle, same settings) stalls in the valley around (0.6, 0.37): same behaviour expected
     assert 0.4 <= sol[0] <= 1.1 and abs(sol[1] - sol[0] ** 2) < 0.05, sol
     assert -((1 - sol[0]) ** 2 + 100 * (sol[1] - sol[0] ** 2) ** 2) > -0.5  # objective at x0 = (0, 0) is -1
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16_tc"])
+@pytest.mark.parametrize("ts1", ["perms", "tile_shuffle"])
+def test_reference_known_answer_closed_form(golden_dir, precision, ts1):
+    """The reference's known-answer test of evaluate_action_sequences (tests/core/test_models.py:365-385):
+    next_obs = obs + a, reward = next_obs => return = H(H+1)/2 * a for H, P in 1..9, a in {1, 2}, bit-exact.
+    The model is the hand-built ReLU ensemble the imported reference was run on (tests/golden/kat_counter_world.npz)."""
+    import mbrl_lib_b200 as bp
+    from mbrl_lib_b200 import functions
+
+    spec, arrays = syn.counter_world()
+    gold = np.load(os.path.join(golden_dir, "kat_counter_world.npz"))
+    assert str(gold["model_sum"]) == syn.checksum(arrays)
+    model = bp.model_from_arrays(spec, arrays, DEV)
+    env = bp.ModelEnv(_Env(spec), model, functions.no_termination, None, generator=torch.Generator(device=DEV),
+                      precision=precision, ts1=ts1)
+    N = 4
+    for P in range(1, 10):
+        for H in range(1, 10):
+            for a in (1.0, 2.0):
+                ret = env.evaluate_action_sequences(torch.full((N, H, 1), a, device=DEV), np.zeros(1), P)
+                want = gold["returns"][P - 1, H - 1, int(a) - 1]
+                assert want == H * (H + 1) / 2 * a
+                assert torch.equal(ret.cpu(), torch.full((N,), float(want))), (P, H, a, ret)

@@ -130,22 +130,28 @@ def test_cem_over_model_matches_reference(golden_dir):
     np.testing.assert_allclose(sol.numpy(), g["solution"], rtol=1e-6, atol=1e-7)
 
 
-def test_reference_known_answer_dummy_model():
+def test_reference_known_answer_dummy_model(golden_dir):
     """The reference's only known-answer test of evaluate_action_sequences (tests/core/test_models.py:365-385):
-    next_obs = obs + mean(act), reward = next_obs  =>  return = H(H+1)/2 * a.  Restated on the oracle's rollout
-    loop with a closed-form 'model': a linear 1-member deterministic MLP cannot express it exactly, so we check
-    the accumulation / particle-mean logic directly."""
-    for P in range(1, 5):
-        for H in range(1, 6):
+    next_obs = obs + act, reward = next_obs  =>  return = H(H+1)/2 * a.  The dummy model is expressed as a
+    hand-built ReLU ensemble (synthetic.counter_world) so the whole oracle path runs: model input, member
+    routing by permutation, delta targets, learned-reward column, accumulation and the particle mean."""
+    spec, arrays = syn.counter_world()
+    gold = _load(golden_dir, "kat_counter_world.npz")  # the imported reference on the same hand-built model
+    assert str(gold["model_sum"]) == syn.checksum(arrays)
+    m = po.OracleModel(spec, arrays)
+    g = np.random.default_rng(0)
+    N = 4
+    for P in range(1, 10):
+        for H in range(1, 10):
             for a in (1.0, 2.0):
-                N = 3
-                total = torch.zeros(N * P, 1)
-                obs = torch.zeros(N * P, 1)
-                for t in range(H):
-                    obs = obs + a
-                    total += obs
-                ret = total.reshape(-1, P).mean(dim=1)
-                assert torch.allclose(ret, torch.full((N,), H * (H + 1) / 2 * a))
+                B = N * P
+                actions = torch.full((N, H, 1), a)
+                perms = torch.from_numpy(np.stack([g.permutation(B) for _ in range(H)]))
+                for bf16 in (False, True):
+                    m.emulate_bf16 = bf16
+                    ret = m.evaluate_action_sequences(actions, np.zeros(1), P, perms, None)
+                    assert torch.equal(ret, torch.full((N,), H * (H + 1) / 2 * a)), (P, H, a, bf16)
+                    assert ret[0].item() == gold["returns"][P - 1, H - 1, int(a) - 1]
 
 
 def test_bf16_emulation_tolerance_band():
