@@ -65,10 +65,16 @@ __device__ __forceinline__ uint32_t a_chunk_off(int i, int kc) { return (uint32_
 // layer-0 operand of one step -> activation buffer in TMEM: normalise(cat(proc(obs), act)), two constant-one bias
 // columns, zero pad.  Branch-free for obs_process == NONE (clamped loads + selects), generic otherwise.  Not inlined:
 // executed once per horizon step, and the kernel's code size matters (instruction cache).
-static __device__ __noinline__ void build_input_tmem(const ModelDev& m, const float* my_obs, const float* arow,
+// The model dimensions come in BY VALUE: a `const ModelDev&` here made the compiler keep a per-thread copy of the
+// whole parameter struct in local memory (464 B x 576 threads, far more than the L1 left beside 200 KB of shared
+// memory), and every field read in the step loop became an L2 round trip.
+struct InDims {
+  int Kp0, D, Dp, A, in, obs_process;
+};
+static __device__ __noinline__ void build_input_tmem(const InDims m, const float* my_obs, const float* arow,
                                                      const float* c_mean, const float* c_istd, uint32_t a_out, int cs,
                                                      int CS, uint64_t* bar_ar) {
-  const int Kp0 = m.Kp[0];
+  const int Kp0 = m.Kp0;
   for (int ks = cs; ks < Kp0 / 16; ks += CS) {
     float x[16];
     if (m.obs_process == B200PETS_PROC_NONE) {
@@ -251,7 +257,8 @@ static __device__ __noinline__ void cem_tail_refit(const TailArgs* ap, int dims,
 // the two activation buffers (layer g reads buffer g & 1 and its epilogue writes buffer (g + 1) & 1).
 template <int ACT, int CS, bool CEMF>  // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
 __global__ void __launch_bounds__(64 + 128 * CS, 1)
-rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const long long num_tiles) {
+rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ RolloutArgs a, const __grid_constant__ TcPlan p,
+                  const long long num_tiles) {
   constexpr int kEpiThreads = 128 * CS;
   constexpr int kThreadsAll = 64 + kEpiThreads;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -272,6 +279,12 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.nstages;
+  if (a.timeline && threadIdx.x == 64 && (blockIdx.x == 0 || blockIdx.x == 40)) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.timeline[256 + (blockIdx.x ? 8 : 0) + 0] = clock64();  // kernel entry (cycles), wall clock (ns)
+    a.timeline[256 + (blockIdx.x ? 8 : 0) + 1] = gt;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -458,8 +471,9 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
     const bool defer_score = L >= 4;
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
 
+    const InDims in_dims{m.Kp[0], m.D, m.Dp, m.A, m.in, m.obs_process};
     auto build_input = [&](int tt) {
-      build_input_tmem(m, my_obs, act_buf(tt), c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs,
+      build_input_tmem(in_dims, my_obs, act_buf(tt), c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs,
                        CS, bar_ar);
     };
 
@@ -525,6 +539,8 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
         const bool stamp = a.timeline && blockIdx.x == 0 && warp == 2 && lane == 0 && t == a.t0 + 5 && tile == blockIdx.x;
         int sp = 0;
         if (stamp) a.timeline[sp++] = clock64();  // 0: step start (layer-0 operand already handed over)
+        if (a.timeline && warp == 2 && lane == 0 && tile == blockIdx.x && (blockIdx.x == 0 || blockIdx.x == 40) && t - a.t0 < 60)
+          a.timeline[128 + (blockIdx.x ? 64 : 0) + (t - a.t0)] = clock64();  // coarse: every step start of two CTAs
         const bool more = t + 1 < a.t1;
         if (owner && act_regs && more) {  // global loads complete under the layers (not in fused-CEM mode)
           const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
@@ -699,6 +715,12 @@ rollout_tc_kernel(const ModelDev m, const RolloutArgs a, const TcPlan p, const l
 
   tc_fence_before();
   __syncthreads();
+  if (a.timeline && threadIdx.x == 64 && (blockIdx.x == 0 || blockIdx.x == 40)) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.timeline[256 + (blockIdx.x ? 8 : 0) + 2] = clock64();  // all tiles of this CTA done
+    a.timeline[256 + (blockIdx.x ? 8 : 0) + 3] = gt;
+  }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
   // ---- fused CEM iteration: the last CTA to get here refits the sampling distribution ----
   if (CEMF && a.tail_counter) {

@@ -9,7 +9,7 @@ spec, arrays, env = bench.build_problem("cuda:0")
 inp = syn.make_rollout_inputs(spec, with_noise=False)
 acts = torch.from_numpy(inp["actions"]).to("cuda:0")
 lib = _lib.load()
-buf = torch.zeros(128, dtype=torch.int64, device="cuda:0")
+buf = torch.zeros(512, dtype=torch.int64, device="cuda:0")
 for _ in range(3):
     env.evaluate_action_sequences(acts, inp["obs0"], spec.particles)
 lib.b200pets_debug_timeline(_lib.ptr(buf))
@@ -23,3 +23,13 @@ print("fine stamps:", [x - t0 for x in b[40:56] if x])
 for l in range(5):
     s = b[64 + 4 * l: 68 + 4 * l]
     print(f"mma layer {l}: starts waiting {s[0]-t0}, weights + first activation half ready {s[1]-t0}, all MMAs issued {s[3]-t0}")
+
+for name, base, kb in (("CTA 0", 128, 256), ("CTA 40", 192, 264)):
+    st = [x for x in b[base:base + 60] if x]
+    k0, g0, k1, g1 = b[kb:kb + 4]
+    if not st or not k0:
+        continue
+    d = [st[i + 1] - st[i] for i in range(len(st) - 1)]
+    print(f"coarse {name}: kernel entry -> first step start {st[0] - k0} cycles; step periods {d}")
+    print(f"coarse {name}: last step start -> CTA done {k1 - st[-1]} cycles; CTA total {k1 - k0} cycles = {g1 - g0} ns "
+          f"=> {1e3 * (k1 - k0) / max(g1 - g0, 1):.0f} MHz")
