@@ -108,15 +108,22 @@ __device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0, 1)
 }
 
 // four N(0,1) draws from one Philox block (not inlined: ~150 instructions, called from several cold places)
-static __device__ __noinline__ void philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               unsigned long long seed, float out[4]) {
+// Not inlined (code size), result returned BY VALUE in registers: an out-pointer would put the caller's array in
+// local memory, which misses the small L1 left beside the shared-memory carve-out.
+static __device__ __noinline__ float4 philox_normal4v(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  unsigned long long seed) {
   U4 r = philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
   float u0 = u32_to_unit(r.x), u1 = u32_to_unit(r.y), u2 = u32_to_unit(r.z), u3 = u32_to_unit(r.w);
   float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
   float s0, c0f, s1, c1f;
   __sincosf(6.283185307179586f * u1, &s0, &c0f);
   __sincosf(6.283185307179586f * u3, &s1, &c1f);
-  out[0] = r0 * c0f; out[1] = r0 * s0; out[2] = r1 * c1f; out[3] = r1 * s1;
+  return make_float4(r0 * c0f, r0 * s0, r1 * c1f, r1 * s1);
+}
+__device__ __forceinline__ void philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, unsigned long long seed,
+                                               float out[4]) {
+  const float4 v = philox_normal4v(c0, c1, c2, c3, seed);
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
 }
 
 // RNG stream tags (third counter word, high bits)

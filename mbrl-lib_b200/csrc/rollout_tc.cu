@@ -547,11 +547,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
 #pragma unroll
           for (int j = 0; j < 8; ++j) an[j] = (valid && j < m.A) ? ap[j] : 0.f;
         }
-        float zpre[2][4];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) zpre[u][e] = 0.f;
+        float zpre0[4] = {0.f, 0.f, 0.f, 0.f}, zpre1[4] = {0.f, 0.f, 0.f, 0.f};  // statically indexed: registers
 
         // ---- hidden layers: accumulator half -> activation -> bf16 pairs -> next layer's A operand in TMEM ----
         for (int l = 0; l < L; ++l, ++g) {
@@ -607,7 +603,10 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
               float z4[4];
               philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z4);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) zpre[l & 1][e] = z4[e];
+              for (int e = 0; e < 4; ++e) {
+                if (l == 0) zpre0[e] = z4[e];
+                else zpre1[e] = z4[e];
+              }
             }
             // previous step's reward / termination, off the critical path (the scorer thread has no noise group here)
             if (l == 1 && scorer && t > a.t0 && defer_score) score(t - 1);
@@ -661,7 +660,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
               }
             } else if (u < 2 && u < L) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) z[e] = u == 0 ? zpre[0][e] : zpre[1][e];
+              for (int e = 0; e < 4; ++e) z[e] = u == 0 ? zpre0[e] : zpre1[e];
             } else {
               philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z);
             }

@@ -18,7 +18,7 @@ torch.cuda.synchronize()
 lib.b200pets_debug_timeline(None)
 b = buf.cpu().tolist()
 t0 = b[0]
-print("epilogue thread stamps (cycles since step start):", [x - t0 for x in b[:20] if x])
+print("epilogue thread stamps (cycles since step start):", [x - t0 for x in b[:24] if x])
 print("fine stamps:", [x - t0 for x in b[40:56] if x])
 for l in range(5):
     s = b[64 + 4 * l: 68 + 4 * l]
