@@ -7,12 +7,12 @@ Extra keyword-only knobs choose the arithmetic (``precision``) and how TS1 draws
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional
 
 import numpy as np
 import torch
 
-from . import _lib, functions
+from . import _lib
 from .staging import StagedModel
 
 

@@ -14,7 +14,7 @@ Reference lines each function follows are cited per function (paths relative to 
 from __future__ import annotations
 
 import math
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, Optional, Tuple
 
 import numpy as np
 import torch

@@ -4,8 +4,6 @@ on every rank as a top-k over the union population."""
 import os
 import socket
 
-import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
