@@ -34,6 +34,9 @@ WORKLOAD = "halfcheetah"  # BASELINE.json configs[1]
 CEM_ITERS, ELITE_RATIO, ALPHA = 5, 0.1, 0.1
 FLOP_PER_SEQ = 157.68e6  # 2 * sum K*N (true dims) * P * H = 262 800 * 20 * 30
 METRIC = "candidate action-sequences/sec, PETS HalfCheetah CEM"
+# the same workload string on both arms (ours and --impl reference)
+WORKLOAD_DESC = ("PETS gym___HalfCheetah-v4 dims (obs 17, act 6): ensemble 7 (5 elites) x 4x200 SiLU, CEM pop 500 x 5 iterations "
+                 "per plan, horizon 30, 20 particles, TS1")
 NCU_DRAM_BYTES_PER_LAUNCH = 1936896 + 188416  # measured once per change with ncu (see profiles/), not at bench time
 
 
@@ -263,9 +266,8 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if env.precision == "bf16_tc" else "f32",
             "data": "synthetic",
-            "config": {"workload": "PETS gym___HalfCheetah-v4 dims (obs 17, act 6): ensemble 7 (5 elites) x 4x200 SiLU, "
-                                   "CEM pop 500 x 5 iterations per step, horizon 30, 20 particles, TS1 (in-kernel tile shuffle)",
-                       "population_per_gpu": N, "sequences_per_step": seqs_per_step, "parallelism": f"population-sharded x{world}",
+            "config": {"workload": WORKLOAD_DESC, "step": "one 5-iteration CEM plan (2 500 sequences per GPU)",
+                       "ts1": "in-kernel tile shuffle", "population_per_gpu": N, "sequences_per_step": seqs_per_step, "parallelism": f"population-sharded x{world}",
                        "l2": "flushed between timed steps (256 MB write, untimed); weights (1.3 MB) are re-fetched every step",
                        "precision": env.precision},
             "gpu_launches": launches_per_step * args.steps,
@@ -368,8 +370,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "sequences/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": steps, "warmup": min(max(args.warmup, 1), 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PETS gym___HalfCheetah-v4 dims: ensemble 7 (5 elites) x 4x200 SiLU, pop 500, horizon 30, 20 particles, TS1",
-                   "device": "cpu"},
+        "config": {"workload": WORKLOAD_DESC, "step": "bounded sample: one CEM iteration's evaluation (500 sequences)",
+                   "ts1": "torch.randperm per step (the reference's rule)", "device": "cpu"},
         "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
