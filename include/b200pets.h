@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200PETS_VERSION 1
+#define B200PETS_VERSION 2
 
 /* error codes */
 #define B200PETS_OK 0
@@ -71,8 +71,10 @@ extern "C" {
 
 /* how TS1 assigns rows to members when no permutation is injected */
 #define B200PETS_TS1_PERMS 0        /* explicit permutations (one per step), reference semantics */
-#define B200PETS_TS1_TILE_SHUFFLE 1 /* in-kernel: every 128-row tile draws one member per step; the particles
-                                       of a sequence sit in different tiles (DESIGN.md "TS1 in production") */
+#define B200PETS_TS1_TILE_SHUFFLE 1 /* in-kernel: a shuffle group = the particle-p copies of 128 consecutive (global)
+                                       sequences; every (group, step) draws one member uniformly from Philox, so the
+                                       particles of one sequence (different groups) draw independently, as rows do
+                                       under the reference's randperm split (DESIGN.md "TS1 in production") */
 
 typedef struct b200pets_model_s* b200pets_model_t;
 
@@ -131,12 +133,19 @@ typedef struct {
   int32_t ts1_mode;    /* B200PETS_TS1_* (only read for PROP_RANDOM_MODEL with perms == NULL) */
   uint64_t seed;       /* Philox key of in-kernel draws */
   uint64_t offset;     /* Philox stream offset; callers advance it per call */
+  /* population sharded over GPUs: this call evaluates global sequences
+   * [first_sequence, first_sequence + population) of a population of global_population (0 = population, i.e. one GPU).
+   * Every in-kernel draw (population noise, model noise, member per shuffle group) is keyed by GLOBAL sequence
+   * index, so results do not depend on the number of GPUs. */
+  int32_t first_sequence;
+  int32_t global_population;
 } b200pets_rollout_cfg;
 
 /* ModelEnv.evaluate_action_sequences (mbrl/models/model_env.py:145-191).
  *   obs0    [dev] float[D]          initial_state (already cast to fp32, model_env.py:173)
  *   actions [dev] float[N][H][A]
- *   perms   [dev] int64: TS1 [H][B], TSinf [1][B]; NULL = draw in kernel (TS1: cfg.ts1_mode; TSinf: balanced)
+ *   perms   [dev] int64: TS1 [H][B], TSinf [1][B]; NULL = draw in kernel (shuffle groups, see
+ *           b200pets_shuffle_member_map: per step for TS1, once for TSinf)
  *   eps     [dev] float[H][B][out] injected N(0,1) model noise or NULL = Philox in kernel
  *   returns [dev] float[N]          mean over particles of the summed rewards
  *   row_returns [dev] float[B] or NULL: per-particle totals (row r = n*P + p) */
@@ -144,6 +153,15 @@ size_t b200pets_eval_workspace_bytes(b200pets_model_t model, const b200pets_roll
 int b200pets_eval_sequences(b200pets_model_t model, const b200pets_rollout_cfg* cfg, const float* obs0,
                             const float* actions, const int64_t* perms, const float* eps, float* returns,
                             float* row_returns, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The member every shuffle group uses at every step when perms == NULL (exactly what the kernels draw; parity
+ * tests feed it to the oracle as a per-row member assignment, gaussian_mlp.py:202-212 with the permutation replaced).
+ * Group g of this shard = (particle p = g / C, chunk c = c_lo + g % C) with C = number of 128-aligned chunks of
+ * global sequence indices that intersect the shard, c_lo = first_sequence / 128; its rows are the particle-p copies
+ * of global sequences 128c .. 128c+127.  members_out [dev] int32[H][num_groups] (TSinf: all steps equal). */
+int64_t b200pets_shuffle_num_groups(const b200pets_rollout_cfg* cfg);
+int b200pets_shuffle_member_map(const b200pets_rollout_cfg* cfg, int32_t num_members, int32_t* members_out,
+                                void* stream);
 
 /* ModelEnv.step (mbrl/models/model_env.py:87-140) for a batch of B independent states.
  *   perm [dev] int64[B]; NULL is allowed for TS1 (tile shuffle) and expectation; TSinf requires the caller's
@@ -162,6 +180,12 @@ int b200pets_step(b200pets_model_t model, int32_t precision, int32_t propagation
 int b200pets_cem_sample(int32_t population, int32_t dims, const float* mu, const float* dispersion,
                         const float* lower, const float* upper, const float* z, uint64_t seed,
                         uint64_t offset, int32_t clipped_normal, float* population_out, void* stream);
+/* Same for one shard of a population split over GPUs: rows are global sequences first_sequence .. +population-1 and
+ * the Philox draws are keyed by the global index (identical numbers whatever the number of shards). */
+int b200pets_cem_sample_shard(int32_t population, int32_t first_sequence, int32_t dims, const float* mu,
+                              const float* dispersion, const float* lower, const float* upper, const float* z,
+                              uint64_t seed, uint64_t offset, int32_t clipped_normal, float* population_out,
+                              void* stream);
 
 /* One refit: NaN -> -1e-10, top-k, mean / variance of the elites, momentum, best-so-far
  * (trajectory_opt.py:130-140, 178-186; iCEM 474-486 with unbiased = 0).

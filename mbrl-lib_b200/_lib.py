@@ -32,7 +32,8 @@ class ModelDesc(C.Structure):
 
 class RolloutCfg(C.Structure):
     _fields_ = [("population", C.c_int32), ("horizon", C.c_int32), ("particles", C.c_int32), ("precision", C.c_int32),
-                ("propagation", C.c_int32), ("ts1_mode", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64)]
+                ("propagation", C.c_int32), ("ts1_mode", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("first_sequence", C.c_int32), ("global_population", C.c_int32)]
 
 
 class CemCfg(C.Structure):
@@ -57,6 +58,10 @@ _SIGNATURES = {
     "b200pets_step": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32,
                                 _P, _P, _P, _P]),
     "b200pets_cem_sample": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32, _P, _P]),
+    "b200pets_cem_sample_shard": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32,
+                                            _P, _P]),
+    "b200pets_shuffle_num_groups": (C.c_int64, [C.POINTER(RolloutCfg)]),
+    "b200pets_shuffle_member_map": (C.c_int, [C.POINTER(RolloutCfg), C.c_int32, _P, _P]),
     "b200pets_cem_update_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "b200pets_cem_update": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P, C.c_size_t, _P]),

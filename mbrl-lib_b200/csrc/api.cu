@@ -62,7 +62,7 @@ __global__ void gather_members_kernel(const float* __restrict__ src, float* __re
 // the output layer's logvar columns are moved to start at column outp.
 __global__ void pack_image_kernel(const float* __restrict__ Wg, const float* __restrict__ bg, unsigned char* __restrict__ img,
                                   unsigned member_stride, unsigned layer_off, int M, int K, int N, int Kp, int Np,
-                                  int out, int outp, int is_last, int deterministic) {
+                                  int out, int outp, int is_last, int deterministic, float scale) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per = (long long)Kp * Np;
   if (idx >= (long long)M * per) return;
@@ -86,6 +86,7 @@ __global__ void pack_image_kernel(const float* __restrict__ Wg, const float* __r
       v = (k == K) ? hi : (b - hi);
     }
   }
+  v *= scale;  // 0.5 for layers whose output feeds a SiLU (exact: a power of two commutes with bf16 rounding)
   const size_t off = (size_t)m * member_stride + layer_off + ((size_t)(k >> 3) * (Np >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2;
   *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
 }
@@ -141,7 +142,8 @@ static int stage_model(b200pets_model_s* mdl, const float* const* weights, const
       const long long tot = (long long)d.num_members * v.Kp[l] * v.Np[l];
       pack_image_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
           Wg, bg, mdl->blob + mdl->off_img, v.img_member_stride, v.img_layer_off[l], d.num_members, v.K[l], v.N[l], v.Kp[l],
-          v.Np[l], d.out_size, v.outp, l == layers - 1, d.deterministic);
+          v.Np[l], d.out_size, v.outp, l == layers - 1, d.deterministic,
+          (l < layers - 1 && d.activation == B200PETS_ACT_SILU) ? 0.5f : 1.0f);
     }
   }
   if (mdl->tc_ok)
@@ -273,6 +275,15 @@ int b200pets_model_supports_tc(b200pets_model_t model) { return model && model->
 // ---------------------------------------------------------------------------------------------------------
 static long long* g_timeline = nullptr;
 
+static int shard_of(const b200pets_rollout_cfg* cfg, int* seq0, int* n_glob) {
+  *seq0 = cfg->first_sequence;
+  *n_glob = cfg->global_population > 0 ? cfg->global_population : cfg->population;
+  if (*seq0 < 0 || (long long)*seq0 + cfg->population > (long long)*n_glob)
+    return b200pets_set_error(B200PETS_EINVAL, "shard [%d, %d) outside the global population %d", *seq0,
+                              *seq0 + cfg->population, *n_glob);
+  return B200PETS_OK;
+}
+
 static int dispatch(const b200pets_model_s* mdl, int precision, const RolloutArgs& a_in, cudaStream_t stream) {
   RolloutArgs a = a_in;
   a.timeline = g_timeline;
@@ -315,7 +326,8 @@ int b200pets_eval_sequences(b200pets_model_t model, const b200pets_rollout_cfg* 
   a.N = N; a.H = H; a.P = P; a.B = B;
   a.propagation = cfg->propagation;
   a.sample = 1;
-  a.seed = cfg->seed; a.offset = cfg->offset;
+  a.seed = rng_key(cfg->seed, cfg->offset); a.offset = cfg->offset;
+  { int rcs = shard_of(cfg, &a.seq0, &a.n_glob); if (rcs) return rcs; }
   a.act = actions; a.act_div = P; a.act_row_stride = (long long)H * d.act_dim; a.act_t_stride = d.act_dim;
   a.obs0 = obs0;
   a.total_state = total; a.dead_state = dead;
@@ -371,7 +383,8 @@ int b200pets_step(b200pets_model_t model, int32_t precision, int32_t propagation
   a.t0 = 0; a.t1 = 1;
   a.propagation = propagation;
   a.sample = sample;
-  a.seed = seed; a.offset = offset;
+  a.seed = rng_key(seed, offset); a.offset = offset;
+  a.seq0 = 0; a.n_glob = (int)batch;
   a.act = act; a.act_div = 1; a.act_row_stride = d.act_dim; a.act_t_stride = 0;
   a.eps = eps;
   a.init_from_obs0 = 0; a.load_state = 0; a.store_state = 1;
@@ -455,8 +468,8 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
       // B200PETS_CEM_SAMPLE_IN_KERNEL=1 also draws the population inside the rollout kernel (1 launch per iteration,
       // measured slower: every particle row re-derives its sequence's actions on the epilogue's critical path)
       if (!sample_in_kernel) {
-        int rcs = b200pets_cem_sample(N, dims, mu, disp, lower, upper, nullptr, rcfg->seed, rcfg->offset * 1024 + it,
-                                      ccfg->clipped_normal, pop, stream);
+        int rcs = b200pets_cem_sample_shard(N, rcfg->first_sequence, dims, mu, disp, lower, upper, nullptr, rcfg->seed,
+                                            rcfg->offset * 1024 + it, ccfg->clipped_normal, pop, stream);
         if (rcs) return rcs;
       }
       unsigned char* ews = reinterpret_cast<unsigned char*>(eval_ws);
@@ -467,7 +480,8 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
       a.propagation = rcfg->propagation;
       a.slot_mode = rcfg->propagation == B200PETS_PROP_RANDOM_MODEL ? 1 : 2;
       a.sample = 1;
-      a.seed = rcfg->seed; a.offset = rcfg->offset * 1024 + it;
+      a.offset = rcfg->offset * 1024 + it; a.seed = rng_key(rcfg->seed, a.offset);
+      { int rcs = shard_of(rcfg, &a.seq0, &a.n_glob); if (rcs) return rcs; }
       a.eps = eps ? eps + (size_t)it * H * B * model->desc.out_size : nullptr;
       a.obs0 = obs0; a.init_from_obs0 = 1; a.store_state = 1;
       a.total_state = reinterpret_cast<float*>(ews + o1);
@@ -487,8 +501,9 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
       if (values_out) CUDA_TRY(cudaMemcpyAsync(values_out + (size_t)it * N, values, sizeof(float) * N, cudaMemcpyDeviceToDevice, stream));
       continue;
     }
-    int rc = b200pets_cem_sample(N, dims, mu, disp, lower, upper, z ? z + (size_t)it * N * dims : nullptr, rcfg->seed,
-                                 rcfg->offset * 1024 + it, ccfg->clipped_normal, pop, stream);
+    int rc = b200pets_cem_sample_shard(N, rcfg->first_sequence, dims, mu, disp, lower, upper,
+                                       z ? z + (size_t)it * N * dims : nullptr, rcfg->seed, rcfg->offset * 1024 + it,
+                                       ccfg->clipped_normal, pop, stream);
     if (rc) return rc;
     b200pets_rollout_cfg rc_it = *rcfg;
     rc_it.offset = rcfg->offset * 1024 + it;
@@ -503,6 +518,40 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
     if (rc) return rc;
   }
   CUDA_TRY(cudaMemcpyAsync(solution, ccfg->return_mean_elites ? mu : best_sol, sizeof(float) * dims, cudaMemcpyDeviceToDevice, stream));
+  return B200PETS_OK;
+}
+
+namespace {
+__global__ void member_map_kernel(RolloutArgs a, int M, int H, long long groups, int32_t* out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= groups * H) return;
+  const int t = (int)(idx / groups);
+  const long long g = idx % groups;
+  const ShuffleGeom geom = shuffle_geom(a.seq0, a.N, a.n_glob);
+  out[idx] = shuffle_member(a.seed, a.offset, a.slot_mode, shuffle_global_group(geom, g), t, M);
+}
+}  // namespace
+
+int64_t b200pets_shuffle_num_groups(const b200pets_rollout_cfg* cfg) {
+  if (!cfg || cfg->population <= 0 || cfg->particles <= 0) return 0;
+  int seq0, n_glob;
+  if (shard_of(cfg, &seq0, &n_glob)) return 0;
+  return (int64_t)cfg->particles * shuffle_geom(seq0, cfg->population, n_glob).C_loc;
+}
+
+int b200pets_shuffle_member_map(const b200pets_rollout_cfg* cfg, int32_t num_members, int32_t* members_out, void* stream) {
+  if (!cfg || !members_out || num_members < 1) return b200pets_set_error(B200PETS_EINVAL, "shuffle_member_map: bad argument");
+  RolloutArgs a{};
+  a.N = cfg->population; a.H = cfg->horizon; a.P = cfg->particles;
+  int rc = shard_of(cfg, &a.seq0, &a.n_glob);
+  if (rc) return rc;
+  a.seed = rng_key(cfg->seed, cfg->offset); a.offset = cfg->offset;
+  a.slot_mode = cfg->propagation == B200PETS_PROP_FIXED_MODEL ? 2 : 1;
+  const long long groups = b200pets_shuffle_num_groups(cfg);
+  const long long tot = groups * cfg->horizon;
+  if (tot <= 0) return b200pets_set_error(B200PETS_EINVAL, "shuffle_member_map: empty configuration");
+  member_map_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, num_members, cfg->horizon, groups, members_out);
+  CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }
 

@@ -14,7 +14,7 @@ namespace {
 __global__ void cem_sample_kernel(int n, int dims, const float* __restrict__ mu, const float* __restrict__ disp,
                                   const float* __restrict__ lb, const float* __restrict__ ub,
                                   const float* __restrict__ z, unsigned long long seed, unsigned long long offset,
-                                  int clipped, float* __restrict__ pop) {
+                                  int clipped, float* __restrict__ pop, int seq0) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n * dims) return;
   const int d = (int)(idx % dims);
@@ -25,7 +25,7 @@ __global__ void cem_sample_kernel(int n, int dims, const float* __restrict__ mu,
   } else {
     // N(0,1); truncated to [-2, 2] by redrawing violators (util/math.py:83-92) unless clipped_normal
     uint32_t attempt = 0;
-    const int n_i = (int)(idx / dims);
+    const int n_i = seq0 + (int)(idx / dims);  // GLOBAL sequence index: draws do not depend on the sharding
     while (true) {
       float g[4];
       philox_normal4((uint32_t)n_i, (uint32_t)(d >> 2), RNG_STREAM_CEM | attempt, (uint32_t)offset, seed, g);
@@ -500,15 +500,25 @@ mppi_update_kernel(int n, int dims, float gamma, const float* __restrict__ pop, 
 // ------------------------------------------------------------------------------------------------------
 extern "C" {
 
+int b200pets_cem_sample_shard(int32_t population, int32_t first_sequence, int32_t dims, const float* mu,
+                              const float* dispersion, const float* lower, const float* upper, const float* z,
+                              uint64_t seed, uint64_t offset, int32_t clipped_normal, float* population_out,
+                              void* stream) {
+  if (population <= 0 || dims <= 0) return b200pets_set_error(B200PETS_EINVAL, "cem_sample: empty population");
+  if (first_sequence < 0) return b200pets_set_error(B200PETS_EINVAL, "cem_sample: negative first_sequence");
+  long long tot = (long long)population * dims;
+  cem_sample_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      population, dims, mu, dispersion, lower, upper, z, rng_key(seed, offset), offset, clipped_normal, population_out,
+      first_sequence);
+  CUDA_TRY(cudaGetLastError());
+  return B200PETS_OK;
+}
+
 int b200pets_cem_sample(int32_t population, int32_t dims, const float* mu, const float* dispersion,
                         const float* lower, const float* upper, const float* z, uint64_t seed, uint64_t offset,
                         int32_t clipped_normal, float* population_out, void* stream) {
-  if (population <= 0 || dims <= 0) return b200pets_set_error(B200PETS_EINVAL, "cem_sample: empty population");
-  long long tot = (long long)population * dims;
-  cem_sample_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      population, dims, mu, dispersion, lower, upper, z, seed, offset, clipped_normal, population_out);
-  CUDA_TRY(cudaGetLastError());
-  return B200PETS_OK;
+  return b200pets_cem_sample_shard(population, 0, dims, mu, dispersion, lower, upper, z, seed, offset, clipped_normal,
+                                   population_out, stream);
 }
 
 size_t b200pets_cem_update_workspace_bytes(int32_t population, int32_t dims, int32_t elite_num) {
@@ -536,11 +546,8 @@ static int run_select(int mode, int n, int dims, int k, float alpha, int unbiase
   if ((size_t)33 * dims * sizeof(float) <= 160 * 1024) {  // partial sums in shared memory (latency-bound reduction)
     dyn = (size_t)33 * dims * sizeof(float);
     s.partial = nullptr;
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(cem_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_set = true;
-    }
+    // the attribute is per device: set it on every call (cheap) rather than caching it per process
+    CUDA_TRY(cudaFuncSetAttribute(cem_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
   cem_select_kernel<<<1, kSelThreads, dyn, (cudaStream_t)stream>>>(s);
   CUDA_TRY(cudaGetLastError());
@@ -578,7 +585,7 @@ int b200pets_icem_sample(int32_t n, int32_t horizon, int32_t act_dim, float expo
   if ((sr == nullptr) != (si == nullptr)) return b200pets_set_error(B200PETS_EINVAL, "icem_sample: sr and si go together");
   long long tot = (long long)n * act_dim;
   icem_sample_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      n, horizon, act_dim, exponent, mu, var, lower, upper, sr, si, seed, offset, population_out);
+      n, horizon, act_dim, exponent, mu, var, lower, upper, sr, si, rng_key(seed, offset), offset, population_out);
   CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }
@@ -589,7 +596,7 @@ int b200pets_icem_append_elites(int32_t keep, int32_t horizon, int32_t act_dim, 
   if (keep <= 0) return B200PETS_OK;
   int tot = keep * horizon * act_dim;
   icem_append_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      keep, horizon, act_dim, elite, reinterpret_cast<const long long*>(index), shift, mu, var, end_eps, seed, offset, dst);
+      keep, horizon, act_dim, elite, reinterpret_cast<const long long*>(index), shift, mu, var, end_eps, rng_key(seed, offset), offset, dst);
   CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }
@@ -601,7 +608,7 @@ int b200pets_mppi_sample(int32_t population, int32_t horizon, int32_t act_dim, f
   if (population <= 0 || horizon <= 0 || act_dim <= 0) return b200pets_set_error(B200PETS_EINVAL, "mppi_sample: empty population");
   long long tot = (long long)population * act_dim;
   mppi_sample_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      population, horizon, act_dim, beta, mean, past_action, lower, upper, z, seed, offset, population_out);
+      population, horizon, act_dim, beta, mean, past_action, lower, upper, z, rng_key(seed, offset), offset, population_out);
   CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }

@@ -42,8 +42,10 @@ struct RolloutArgs {
   int t0, t1;
   int propagation;      // B200PETS_PROP_*
   int slot_mode;        // 0: rid = perm[slot] (or slot if perm == NULL), members own contiguous slot ranges
-                        // 1: tile shuffle: rid = (slot % N) * P + slot / N, member drawn per (tile, step)
-                        // 2: as 1 but the member is drawn once per tile (TSinf without an injected permutation)
+                        // 1: tile shuffle (see "tile shuffle" below): member drawn per (shuffle group, step)
+                        // 2: as 1 but the member is drawn once per group (TSinf without an injected permutation)
+  int seq0;             // tile shuffle: global index of this shard's first sequence (0 on one GPU)
+  int n_glob;           // tile shuffle: global population (= N on one GPU); fixes the global group numbering
   const long long* perm;   // [B] for this launch or NULL
   const float* eps;        // [t1-t0][B][out] for this launch (row-id indexed) or NULL -> Philox
   int sample;              // 0: mean prediction
@@ -238,17 +240,74 @@ static __device__ __noinline__ bool term_eval(int fn, const float* o, int D, int
   }
 }
 
-// slot -> row id and tile -> member bookkeeping shared by both rollout kernels
-__device__ __forceinline__ long long slot_to_rid(const RolloutArgs& a, long long slot) {
-  if (a.slot_mode >= 1) return (slot % a.N) * (long long)a.P + slot / a.N;
+// ------------------------------------------------------------------------------------------------------
+// Row bookkeeping shared by both rollout kernels.
+//
+// slot_mode 0 (explicit permutation, the reference's rule gaussian_mlp.py:202-212): member m owns slots
+// [m*B/M, (m+1)*B/M), row id = perm[slot].
+//
+// slot_mode >= 1 ("tile shuffle"): a shuffle GROUP is (particle p, 128-aligned chunk c of GLOBAL sequence
+// indices): its rows are the particle-p copies of sequences 128c .. 128c+127.  Groups are numbered globally
+// gt = p * C_glob + c (C_glob = ceil(global population / 128)), so that the member a row uses and its noise
+// stream depend on (global sequence, particle, step, seed, offset) only -- not on how the population is sharded
+// over GPUs.  A shard [seq0, seq0 + N) holds the chunks c_lo .. c_hi that intersect it; rows of a boundary chunk
+// that belong to another shard are simply invalid here.  Local tile index = p * C_loc + (c - c_lo).
+// Members: every (group, step) draws one member uniformly and independently from Philox keyed by (gt, t, seed,
+// offset).  A row's member at a step is therefore uniform over the M elite members, and the 20 particles of one
+// sequence (which sit in 20 different groups) draw independently of each other -- the law of the reference's rule for a
+// row (randperm split, gaussian_mlp.py:202-206) up to its without-replacement coupling across the B rows, which is
+// O(M / B) per pair of rows.  What is NOT reproduced: the exact balance (each member exactly B/M rows per step), and
+// the 128 same-particle neighbours of a group share the draw (common random numbers across candidates).
+// ------------------------------------------------------------------------------------------------------
+#define B200PETS_GROUP_ROWS 128
+
+struct ShuffleGeom {
+  int c_lo, C_loc, C_glob;
+};
+
+__host__ __device__ __forceinline__ ShuffleGeom shuffle_geom(int seq0, int N, int n_glob) {
+  ShuffleGeom g;
+  g.c_lo = seq0 / B200PETS_GROUP_ROWS;
+  g.C_loc = (seq0 + N - 1) / B200PETS_GROUP_ROWS - g.c_lo + 1;
+  g.C_glob = (n_glob + B200PETS_GROUP_ROWS - 1) / B200PETS_GROUP_ROWS;
+  return g;
+}
+
+// local group index -> global group number
+__device__ __forceinline__ long long shuffle_global_group(const ShuffleGeom& g, long long group) {
+  const long long p = group / g.C_loc;
+  const int c = g.c_lo + (int)(group % g.C_loc);
+  return p * g.C_glob + c;
+}
+
+// row `i` (0..127) of local group `group`: local row id (n_local * P + p), validity, global row id (RNG key)
+__device__ __forceinline__ long long shuffle_row(const RolloutArgs& a, const ShuffleGeom& g, long long group, int i,
+                                                 bool* valid, long long* rid_glob) {
+  const long long p = group / g.C_loc;
+  const int c = g.c_lo + (int)(group % g.C_loc);
+  const long long ng = (long long)c * B200PETS_GROUP_ROWS + i;
+  *valid = ng >= a.seq0 && ng < (long long)a.seq0 + a.N;
+  *rid_glob = ng * a.P + p;
+  return (ng - a.seq0) * a.P + p;
+}
+
+__device__ __forceinline__ long long slot_to_rid(const RolloutArgs& a, long long slot) {  // slot_mode 0 only
   return a.perm ? a.perm[slot] : slot;
 }
 
-__device__ __forceinline__ int shuffle_member(const RolloutArgs& a, int tile, int t, int M) {
-  if (a.slot_mode == 2) t = 0;
-  U4 r = philox4x32_10((uint32_t)tile, (uint32_t)t, RNG_STREAM_MEMBER, (uint32_t)a.offset, (uint32_t)a.seed,
-                       (uint32_t)(a.seed >> 32));
+// member of global group `gt` at step t: an independent uniform draw per (group, step) from Philox
+__device__ __forceinline__ int shuffle_member(unsigned long long seed, unsigned long long offset, int slot_mode,
+                                              long long gt, int t, int M) {
+  if (slot_mode == 2) t = 0;
+  U4 r = philox4x32_10((uint32_t)gt, (uint32_t)t, RNG_STREAM_MEMBER, (uint32_t)offset, (uint32_t)seed,
+                       (uint32_t)(seed >> 32) ^ (uint32_t)(gt >> 32));
   return (int)(((unsigned long long)r.x * (unsigned long long)M) >> 32);
+}
+
+// Kernels put the low 32 bits of the stream offset into a Philox counter word; the high 32 bits go into the key so
+// that long runs (> 2^32 offsets) never replay a stream.  Applied once at every C entry point.
+static inline unsigned long long rng_key(unsigned long long seed, unsigned long long offset) {
+  return seed ^ (offset & 0xFFFFFFFF00000000ull);
 }
 
 // host-side error plumbing (api.cu)

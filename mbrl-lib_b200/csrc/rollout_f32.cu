@@ -93,37 +93,57 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
   float* exp_s = act_s + TR * m.A;          // [TR][nout] (expectation only, else unused but allocated)
   float* tot_s = exp_s + TR * m.nout;       // [TR]
   float* rew_s = tot_s + TR;                // [TR]
-  long long* rid_s = reinterpret_cast<long long*>(rew_s + TR);  // [TR]
-  int* dead_s = reinterpret_cast<int*>(rid_s + TR);             // [TR]
+  long long* rid_s = reinterpret_cast<long long*>(rew_s + TR);  // [TR] local row id (-1: no row)
+  long long* gid_s = rid_s + TR;                                // [TR] global row id (Philox key)
+  int* dead_s = reinterpret_cast<int*>(gid_s + TR);             // [TR]
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
   const bool expectation = a.propagation == B200PETS_PROP_EXPECTATION;
-  long long slot0;
+  // nv: rows of this tile that may hold a row (row i is live iff rid_s[i] >= 0)
   int nv, member = 0;
-  if (expectation || a.slot_mode >= 1) {
-    slot0 = (long long)tile * TR;
-    nv = (int)min((long long)TR, a.B - slot0);
+  const bool shuffle = a.slot_mode >= 1 && !expectation;
+  const ShuffleGeom geom = shuffle_geom(a.seq0, a.N, a.n_glob);
+  constexpr int kSub = B200PETS_GROUP_ROWS / TR;  // tiles per shuffle group
+  const long long group = tile / kSub;
+  if (shuffle) {  // tile = TR consecutive rows of a shuffle group (common.cuh)
+    nv = TR;
+    for (int i = tid; i < TR; i += kThreads) {
+      bool valid;
+      long long gid;
+      const long long rid = shuffle_row(a, geom, group, (tile % kSub) * TR + i, &valid, &gid);
+      rid_s[i] = valid ? rid : -1;
+      gid_s[i] = gid;
+    }
   } else {
-    const long long Bm = a.B / m.M;
-    const int tpm = (int)((Bm + TR - 1) / TR);
-    member = tile / tpm;
-    const int c = tile % tpm;
-    slot0 = (long long)member * Bm + (long long)c * TR;
-    nv = (int)min((long long)TR, Bm - (long long)c * TR);
+    long long slot0;
+    if (expectation) {
+      slot0 = (long long)tile * TR;
+      nv = (int)min((long long)TR, a.B - slot0);
+    } else {
+      const long long Bm = a.B / m.M;
+      const int tpm = (int)((Bm + TR - 1) / TR);
+      member = tile / tpm;
+      const int c = tile % tpm;
+      slot0 = (long long)member * Bm + (long long)c * TR;
+      nv = (int)min((long long)TR, Bm - (long long)c * TR);
+    }
+    for (int i = tid; i < TR; i += kThreads) {
+      rid_s[i] = i < nv ? slot_to_rid(a, slot0 + i) : -1;
+      gid_s[i] = rid_s[i] + (long long)a.seq0 * a.P;
+    }
   }
-  for (int i = tid; i < TR; i += kThreads) rid_s[i] = i < nv ? slot_to_rid(a, slot0 + i) : -1;
   __syncthreads();
 
   // ---- load state -------------------------------------------------------------------------------
   for (int idx = tid; idx < TR * m.D; idx += kThreads) {
     int i = idx / m.D, d = idx % m.D;
     float v = 0.f;
-    if (i < nv) v = a.init_from_obs0 ? a.obs0[d] : a.obs_in[rid_s[i] * m.D + d];
+    if (rid_s[i] >= 0) v = a.init_from_obs0 ? a.obs0[d] : a.obs_in[rid_s[i] * m.D + d];
     obs_s[idx] = v;
   }
   for (int i = tid; i < TR; i += kThreads) {
-    bool ld = a.load_state && i < nv;
+    bool ld = a.load_state && rid_s[i] >= 0;
     tot_s[i] = ld ? a.total_state[rid_s[i]] : 0.f;
     dead_s[i] = ld ? (int)a.dead_state[rid_s[i]] : 0;
   }
@@ -131,12 +151,12 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
 
   const int nlayers = m.L + 1;
   for (int t = a.t0; t < a.t1; ++t) {
-    if (a.slot_mode >= 1 && !expectation) member = shuffle_member(a, tile, t, m.M);
+    if (shuffle) member = shuffle_member(a.seed, a.offset, a.slot_mode, shuffle_global_group(geom, group), t, m.M);
     // ---- actions ------------------------------------------------------------------------------
     for (int idx = tid; idx < TR * m.A; idx += kThreads) {
       int i = idx / m.A, j = idx % m.A;
       float v = 0.f;
-      if (i < nv) v = a.act[(rid_s[i] / a.act_div) * a.act_row_stride + (long long)t * a.act_t_stride + j];
+      if (rid_s[i] >= 0) v = a.act[(rid_s[i] / a.act_div) * a.act_row_stride + (long long)t * a.act_t_stride + j];
       act_s[idx] = v;
     }
     __syncthreads();
@@ -148,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
       for (int idx = tid; idx < TR * inr; idx += kThreads) {
         int i = idx / inr, j = idx % inr;
         float v = 0.f;
-        if (i < nv && j < m.in) {
+        if (rid_s[i] >= 0 && j < m.in) {
           float x = j < m.Dp ? proc_obs_elem(obs_s + i * m.D, j, m.obs_process) : act_s[i * m.A + (j - m.Dp)];
           if (m.norm_mode == 2)
             x = (float)(((double)x - m.norm_mean_d[j]) / m.norm_std_d[j]);
@@ -184,6 +204,7 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
         // ---- prediction -> next observation (in place) ---------------------------------------
         for (int idx = tid; idx < nv * m.out; idx += kThreads) {
           int i = idx / m.out, o = idx % m.out;
+          if (rid_s[i] < 0) continue;
           float mean = cur[i * LD + o];
           float pred = mean;
           if (!m.deterministic && a.sample) {
@@ -196,7 +217,7 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
               e = a.eps[((size_t)(t - a.t0) * a.B + rid_s[i]) * m.out + o];
             } else {
               float z[4];
-              philox_normal4((uint32_t)rid_s[i], (uint32_t)t, RNG_STREAM_EPS | (uint32_t)(o >> 2), (uint32_t)a.offset,
+              philox_normal4((uint32_t)gid_s[i], (uint32_t)t, RNG_STREAM_EPS | (uint32_t)(o >> 2), (uint32_t)a.offset,
                              a.seed, z);
               e = z[o & 3];
             }
@@ -216,6 +237,7 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
       const float invM = 1.0f / (float)m.M;
       for (int idx = tid; idx < nv * m.out; idx += kThreads) {
         int i = idx / m.out, o = idx % m.out;
+        if (rid_s[i] < 0) continue;
         float mean = exp_s[i * m.nout + o] / (float)m.M;
         float pred = mean;
         if (!m.deterministic && a.sample) {
@@ -226,7 +248,7 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
             e = a.eps[((size_t)(t - a.t0) * a.B + rid_s[i]) * m.out + o];
           } else {
             float z[4];
-            philox_normal4((uint32_t)rid_s[i], (uint32_t)t, RNG_STREAM_EPS | (uint32_t)(o >> 2), (uint32_t)a.offset,
+            philox_normal4((uint32_t)gid_s[i], (uint32_t)t, RNG_STREAM_EPS | (uint32_t)(o >> 2), (uint32_t)a.offset,
                            a.seed, z);
             e = z[o & 3];
           }
@@ -244,8 +266,11 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
     }
     // ---- reward, termination, accumulate (model_env.py:124-129, 186-188) ---------------------
     for (int i = tid; i < nv; i += kThreads) {
-      float rew = m.learned_rewards ? rew_s[i]
-                                    : reward_eval(m.reward_fn, act_s + i * m.A, m.A, 1, obs_s + i * m.D, m.D, 1);
+      if (rid_s[i] < 0) continue;
+      // model_env.py:124-128: pred_rewards only when reward_fn is None, an explicit reward_fn always wins
+      float rew = m.reward_fn == B200PETS_REWARD_LEARNED
+                      ? rew_s[i]
+                      : reward_eval(m.reward_fn, act_s + i * m.A, m.A, 1, obs_s + i * m.D, m.D, 1);
       bool done = term_eval(m.term_fn, obs_s + i * m.D, m.D, 1);
       if (a.reward_out) a.reward_out[rid_s[i]] = rew;
       if (a.done_out) a.done_out[rid_s[i]] = done ? 1 : 0;
@@ -260,9 +285,10 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
     if (a.obs_out)
       for (int idx = tid; idx < nv * m.D; idx += kThreads) {
         int i = idx / m.D, d = idx % m.D;
-        a.obs_out[rid_s[i] * m.D + d] = obs_s[idx];
+        if (rid_s[i] >= 0) a.obs_out[rid_s[i] * m.D + d] = obs_s[idx];
       }
     for (int i = tid; i < nv; i += kThreads) {
+      if (rid_s[i] < 0) continue;
       if (a.total_state) a.total_state[rid_s[i]] = tot_s[i];
       if (a.dead_state) a.dead_state[rid_s[i]] = (uint8_t)dead_s[i];
     }
@@ -273,7 +299,8 @@ __global__ void __launch_bounds__(kThreads) rollout_f32_kernel(const ModelDev m,
 
 // number of tiles for a launch (host side)
 static long long f32_num_tiles(const ModelDev& m, const RolloutArgs& a, int TR) {
-  if (a.propagation == B200PETS_PROP_EXPECTATION || a.slot_mode >= 1) return (a.B + TR - 1) / TR;
+  if (a.propagation == B200PETS_PROP_EXPECTATION) return (a.B + TR - 1) / TR;
+  if (a.slot_mode >= 1) return (long long)a.P * shuffle_geom(a.seq0, a.N, a.n_glob).C_loc * (B200PETS_GROUP_ROWS / TR);
   long long Bm = a.B / m.M;
   return (long long)m.M * ((Bm + TR - 1) / TR);
 }
@@ -283,7 +310,7 @@ int launch_rollout_f32(const ModelDev& m, const RolloutArgs& a, cudaStream_t str
   for (int l = 0; l <= m.L; ++l) wmax = max(wmax, m.N[l]);
   const int LD = ((wmax + 3) & ~3) + 4;
   auto smem_for = [&](int TR) {
-    return (size_t)TR * (2 * LD + m.D + m.A + m.nout + 2) * sizeof(float) + (size_t)TR * (sizeof(long long) + sizeof(int));
+    return (size_t)TR * (2 * LD + m.D + m.A + m.nout + 2) * sizeof(float) + (size_t)TR * (2 * sizeof(long long) + sizeof(int));
   };
   int dev = 0, max_smem = 0;
   CUDA_TRY(cudaGetDevice(&dev));

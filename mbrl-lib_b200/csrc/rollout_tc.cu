@@ -32,6 +32,8 @@ struct TcPlan {
   uint32_t tmem_cols;
   int obs_ld, act_ld;
   int h0n;  // columns of the first N half of the hidden layers
+  int kr;   // K-round pipeline with two accumulators (all padded widths <= 208, layer-0 K <= 192)
+  uint32_t off_atail;  // KR: 128 x 16 bf16 tile (K columns 192..207 of the A operand), canonical no-swizzle K-major
   uint32_t smem_bytes;
 };
 
@@ -41,6 +43,9 @@ constexpr int kEpiSplit = 4;  // column splits of the epilogue (16 epilogue warp
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kCemTabDims = 1024;  // horizon * act_dim supported by the fused CEM iteration
+// KR TMEM map: accumulator 0 = [0, 208), accumulator 1 = [208, 416), activations (A operand, K columns 0..191) = [416, 512)
+constexpr uint32_t kAcc1 = 208, kActKR = 416;
+constexpr int kTmemKSteps = 12;  // K steps whose A operand fits the 96 activation columns; later ones come from smem
 
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
@@ -48,12 +53,17 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {  // one MUFU op, no slow-path fix-up (argument is in [1, inf))
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_tc(float x, float slope) {
-  if (ACT == B200PETS_ACT_SILU) {  // x * sigmoid(x) = h + h * tanh(h), h = x / 2  (one MUFU op)
-    float h = 0.5f * x;
-    return fmaf(h, tanh_approx(h), h);
-  }
+  // SiLU: x * sigmoid(x) = h + h * tanh(h) with h = x / 2 (one MUFU op).  The packed weight image of every layer that
+  // feeds a SiLU is pre-scaled by 0.5 (api.cu pack_image_kernel), so the accumulator already holds h.
+  if (ACT == B200PETS_ACT_SILU) return fmaf(x, tanh_approx(x), x);
   if (ACT == B200PETS_ACT_RELU) return fmaxf(x, 0.f);
   return x > 0.f ? x : x * slope;
 }
@@ -73,43 +83,36 @@ struct InDims {
 };
 static __device__ __noinline__ void build_input_tmem(const InDims m, const float* my_obs, const float* arow,
                                                      const float* c_mean, const float* c_istd, uint32_t a_out, int cs,
-                                                     int CS, uint64_t* bar_ar) {
+                                                     int CS, uint64_t* bars, int nbars) {
   const int Kp0 = m.Kp0;
-  for (int ks = cs; ks < Kp0 / 16; ks += CS) {
-    float x[16];
-    if (m.obs_process == B200PETS_PROC_NONE) {
+  // Work unit = 8 operand columns (4 TMEM columns, one tcgen05.st.x4), dealt round-robin to the CS column-split warps
+  // of the row: with Kp0 = 32 every warp has exactly one unit (the 16-column split left half of the warps idle).
+  // j is warp-uniform, so the case analysis below is uniform branching, not divergence; per element: <= 3 LDS,
+  // FADD, FMUL, FADD instead of the ~21 instructions of the clamped-index form.
+  for (int gi = cs; gi < Kp0 / 8; gi += CS) {
+    float x[8];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int j = ks * 16 + e;
-        const int jo = min(j, m.D - 1), ja = min(max(j - m.Dp, 0), m.A - 1), jc = min(j, m.in - 1);
-        const float vo = my_obs[jo], va = arow[ja];
-        const float v = ((j < m.Dp ? vo : va) - c_mean[jc]) * c_istd[jc];
-        x[e] = j < m.in ? v : (j < m.in + 2 ? 1.f : 0.f);
+    for (int e = 0; e < 8; ++e) {
+      const int j = gi * 8 + e;
+      float raw = 0.f, mu = 0.f, is = 0.f, cst = 0.f;
+      if (j < m.in) {
+        if (j < m.Dp) raw = m.obs_process == B200PETS_PROC_NONE ? my_obs[j] : proc_obs_elem(my_obs, j, m.obs_process);
+        else raw = arow[j - m.Dp];
+        mu = c_mean[j];
+        is = c_istd[j];
+      } else if (j < m.in + 2) {
+        cst = 1.f;  // the two bias columns
       }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int j = ks * 16 + e;
-        float v;
-        if (j < m.Dp) {
-          v = (proc_obs_elem(my_obs, j, m.obs_process) - c_mean[j]) * c_istd[j];
-        } else if (j < m.in) {
-          v = (arow[j - m.Dp] - c_mean[j]) * c_istd[j];
-        } else {
-          v = (j < m.in + 2) ? 1.f : 0.f;
-        }
-        x[e] = v;
-      }
+      x[e] = (raw - mu) * is + cst;
     }
-    uint32_t pk[8];
+    uint32_t pk[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(x[2 * e], x[2 * e + 1]);
-    tmem_st8(a_out + (uint32_t)(8 * ks), pk);
+    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(x[2 * e], x[2 * e + 1]);
+    tmem_st4(a_out + (uint32_t)(4 * gi), pk);
   }
   tmem_st_wait();
   tc_fence_before();
-  mbar_arrive(&bar_ar[0]);
-  mbar_arrive(&bar_ar[1]);
+  for (int b = 0; b < nbars; ++b) mbar_arrive(&bars[b]);  // both halves (v3) / every round of layer 0 (KR)
 }
 
 // Actions of (sequence n, step t) drawn from the CEM sampling distribution with exactly the Philox keying of
@@ -255,7 +258,10 @@ static __device__ __noinline__ void cem_tail_refit(const TailArgs* ap, int dims,
 //
 // TMEM columns: [0, 256) accumulators (hidden: halves at 0 and h0n; output layer at 0), [256, 384) and [384, 512)
 // the two activation buffers (layer g reads buffer g & 1 and its epilogue writes buffer (g + 1) & 1).
-template <int ACT, int CS, bool CEMF>  // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
+// KR (K-round pipeline): two accumulators (layer g -> accumulator g & 1), one activation buffer; the epilogue hands the
+// next layer's A operand over in rounds of four 16-column chunks and the MMA warp issues a round's K steps (full N)
+// while the next round's activation pass runs.
+template <int ACT, int CS, bool CEMF, bool KR>  // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
 __global__ void __launch_bounds__(64 + 128 * CS, 1)
 rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ RolloutArgs a, const __grid_constant__ TcPlan p,
                   const long long num_tiles) {
@@ -274,8 +280,10 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* bar_empty = bar_full + kMaxStages;
   uint64_t* bar_ar = bar_empty + kMaxStages;  // [2] activations of half h written (count: all epilogue threads)
-  uint64_t* bar_acc = bar_ar + 2;             // [2] accumulator of half h complete (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
+  uint64_t* bar_acc = bar_ar + 2;             // [2] accumulator of half h complete (tcgen05.commit); KR uses [0] only
+  uint64_t* bar_k = bar_acc + 2;              // [4] KR: activations of round r written (count: all epilogue threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_k + 4);
+  static_assert(!KR || CS == 4, "the K-round pipeline deals chunk 4r + cs to column split cs");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.nstages;
@@ -295,6 +303,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
     mbar_init(&bar_ar[1], kEpiThreads);
     mbar_init(&bar_acc[0], 1);
     mbar_init(&bar_acc[1], 1);
+    for (int r = 0; r < 4; ++r) mbar_init(&bar_k[r], kEpiThreads);
     mbar_fence_init();
   }
   for (int j = threadIdx.x; j < m.in; j += kThreadsAll) {
@@ -334,6 +343,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
   const uint32_t tmem_base = *tmem_slot;
 
   const bool shuffle = a.slot_mode >= 1;
+  const ShuffleGeom geom = shuffle_geom(a.seq0, a.N, a.n_glob);
   const long long Bm = shuffle ? 0 : a.B / m.M;
   const int tpm = shuffle ? 1 : (int)((Bm + kTileM - 1) / kTileM);
   const int nlayers = p.nlayers;
@@ -352,7 +362,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int member = shuffle ? 0 : (int)(tile / tpm);
         for (int t = a.t0; t < a.t1; ++t) {
-          const int mem = shuffle ? shuffle_member(a, (int)tile, t, m.M) : member;
+          const int mem = shuffle ? shuffle_member(a.seed, a.offset, a.slot_mode, shuffle_global_group(geom, tile), t, m.M) : member;
           const uint8_t* base = m.img + (size_t)(blockIdx.x % m.img_replicas) * m.img_replica_stride + (size_t)mem * m.img_member_stride;
           for (int l = 0; l < nlayers; ++l) {
             // one ring slot holds the whole layer image (K core columns contiguous): one barrier, one wait per layer
@@ -374,7 +384,59 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
     // =========================== MMA issuer ===========================
     // The whole warp runs the control flow converged (waits are uniform); the MMAs and commits are issued by the one
     // elected lane, always the same one, so that every tcgen05.commit tracks all MMAs issued before it.
-    {
+    if (KR) {
+      int stage = 0;
+      uint32_t phase = 0, kpar = 0;  // kpar: one parity bit per round barrier
+      uint32_t g = 0;                // global layer counter: selects the accumulator
+      const uint32_t ring_addr = smem_u32(ring);
+      const uint64_t adesc_tail = umma_smem_desc(smem_u32(smem + p.off_atail), 2048u, 128u);
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int t = a.t0; t < a.t1; ++t) {
+          for (int l = 0; l < nlayers; ++l, ++g) {
+            const bool stamp = a.timeline && lane == 0 && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x;
+            const int nk = m.Kp[l] >> 4;
+            const int rounds = (nk + 3) >> 2;
+            const uint32_t np = (uint32_t)m.Np[l];
+            const uint32_t b_lbo = np * 16u;
+            const uint32_t acc = tmem_base + ((g & 1u) ? kAcc1 : 0u);
+            const uint32_t a_col = tmem_base + kActKR;
+            const uint32_t slot_addr = ring_addr + (uint32_t)stage * p.stage_bytes;
+            const uint32_t slot_phase = phase;
+            uint64_t* slot_empty = &bar_empty[stage];
+            uint64_t* slot_full = &bar_full[stage];
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+            const uint32_t idesc = umma_idesc_bf16_m128(np);
+            const uint64_t b_inc = (uint64_t)((2u * b_lbo) >> 4);  // descriptor start-address step per K step
+            if (stamp) a.timeline[64 + l * 4 + 0] = clock64();
+            mbar_wait(slot_full, slot_phase);
+            const uint64_t bdesc = umma_smem_desc(slot_addr, b_lbo, 128u);
+            for (int r = 0; r < rounds; ++r) {
+              mbar_wait(&bar_k[r], (kpar >> r) & 1u);
+              kpar ^= 1u << r;
+              tc_fence_after();
+              if (stamp && r == 0) a.timeline[64 + l * 4 + 1] = clock64();
+              if (elect_one()) {
+                const int k1 = min(4 * r + 4, nk);
+                uint64_t bd = bdesc + (uint64_t)(4 * r) * b_inc;
+                uint32_t acol = a_col + 8u * (uint32_t)(4 * r);
+                for (int kk = 4 * r; kk < k1; ++kk) {
+                  if (kk < kTmemKSteps) umma_bf16_ts(acc, acol, bd, idesc, kk != 0 ? 1u : 0u);
+                  else umma_bf16_ss(acc, adesc_tail, bd, idesc, 1u);  // K columns 192..207 from the shared-memory tile
+                  bd += b_inc;
+                  acol += 8u;
+                }
+                if (r == rounds - 1) {
+                  umma_commit(&bar_acc[0]);
+                  umma_commit(slot_empty);
+                }
+              }
+              __syncwarp();
+            }
+            if (stamp) a.timeline[64 + l * 4 + 3] = clock64();
+          }
+        }
+      }
+    } else {
       int stage = 0;
       uint32_t phase = 0, ar_par = 0;
       uint32_t g = 0;  // global layer counter: selects the activation buffer
@@ -473,30 +535,32 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
 
     const InDims in_dims{m.Kp[0], m.D, m.Dp, m.A, m.in, m.obs_process};
     auto build_input = [&](int tt) {
-      build_input_tmem(in_dims, my_obs, act_buf(tt), c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs,
-                       CS, bar_ar);
+      if (KR) build_input_tmem(in_dims, my_obs, act_buf(tt), c_mean, c_istd, t_lane + kActKR, cs, CS, bar_k,
+                               ((in_dims.Kp0 >> 4) + 3) >> 2);
+      else build_input_tmem(in_dims, my_obs, act_buf(tt), c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs, CS, bar_ar, 2);
     };
 
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      long long slot0;
-      int nv;
+      bool valid;
+      long long rid, rid_glob;  // local row id (n * P + p: indexes actions / state / injected noise), global one (RNG key)
       if (shuffle) {
-        slot0 = tile * kTileM;
-        nv = (int)min((long long)kTileM, a.B - slot0);
+        rid = shuffle_row(a, geom, tile, i, &valid, &rid_glob);
+        if (!valid) rid = 0;
       } else {
         const int member = (int)(tile / tpm);
         const int c = (int)(tile % tpm);
-        slot0 = (long long)member * Bm + (long long)c * kTileM;
-        nv = (int)min((long long)kTileM, Bm - (long long)c * kTileM);
+        const long long slot0 = (long long)member * Bm + (long long)c * kTileM;
+        valid = i < (int)min((long long)kTileM, Bm - (long long)c * kTileM);
+        rid = valid ? slot_to_rid(a, slot0 + i) : 0;
+        rid_glob = rid + (long long)a.seq0 * a.P;
       }
-      const bool valid = i < nv;
-      const long long rid = valid ? slot_to_rid(a, slot0 + i) : 0;
       float tot = 0.f;
       int dead = 0;
       // reward_fn(act_t, obs_{t+1}), termination, dead mask, accumulate (model_env.py:124-129, 186-188): row owner only
       auto score = [&](int ts) {
         const float* arow = act_buf(ts);
-        float rew = m.learned_rewards ? rew_s[i] : reward_eval(m.reward_fn, arow, m.A, 1, my_obs, m.D, 1);
+        // model_env.py:124-128: pred_rewards only when reward_fn is None, an explicit reward_fn always wins
+        float rew = m.reward_fn == B200PETS_REWARD_LEARNED ? rew_s[i] : reward_eval(m.reward_fn, arow, m.A, 1, my_obs, m.D, 1);
         const bool done = term_eval(m.term_fn, my_obs, m.D, 1);
         if (valid) {
           if (a.reward_out) a.reward_out[rid] = rew;
@@ -530,7 +594,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
           for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
         }
       }
-      if (CEMF && sampler) cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, seq_n, a.t0, m.A,
+      if (CEMF && sampler) cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, a.seq0 + seq_n, a.t0, m.A,
                                       act_buf(a.t0), pop_row);
       epi_bar();
       build_input(a.t0);
@@ -554,6 +618,53 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
           const int n_true = m.N[l];
           const int kp_next = m.Kp[l + 1];
           const uint32_t a_out = t_lane + 256u + (((g + 1u) & 1u) << 7);
+          if (KR) {
+            const uint32_t acc_rd = t_lane + ((g & 1u) ? kAcc1 : 0u);
+            mbar_wait(&bar_acc[0], acc0_par);
+            acc0_par ^= 1u;
+            tc_fence_after();
+            if (stamp) a.timeline[sp++] = clock64();  // accumulator ready
+            const int nk_next = kp_next >> 4;
+            const int rounds = (nk_next + 3) >> 2;
+            for (int r = 0; r < rounds; ++r) {
+              const int c = 4 * r + cs;
+              if (c < nk_next) {
+                float v[16];
+                if (16 * c < NpH) {
+                  uint32_t rr[16];
+                  tmem_ld16(acc_rd + (uint32_t)(16 * c), rr);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) v[e] = act_tc<ACT>(__uint_as_float(rr[e]), m.leaky);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                }
+                if (16 * c + 15 >= n_true && 16 * c <= n_true + 1) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) {
+                    const int col = 16 * c + e;
+                    if (col == n_true || col == n_true + 1) v[e] = 1.f;
+                  }
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+                if (c < kTmemKSteps) {
+                  tmem_st8(t_lane + kActKR + (uint32_t)(8 * c), pk);
+                } else {  // K columns 192..207: shared-memory tile of the SS-form K step (two 16-byte core-matrix rows)
+                  uint8_t* at = smem + p.off_atail;
+                  *reinterpret_cast<uint4*>(at + a_chunk_off(i, 0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  *reinterpret_cast<uint4*>(at + a_chunk_off(i, 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                  fence_proxy_async_smem();
+                }
+              }
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(&bar_k[r]);
+              if (stamp && (r == 0 || r + 2 >= rounds)) a.timeline[sp++] = clock64();  // first / last two rounds handed over
+            }
+          } else
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h == 0) {
@@ -601,7 +712,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             const int gq = (CS - 1 - cs) + l * CS;
             if (draw && !a.eps && gq < ngroups) {
               float z4[4];
-              philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z4);
+              philox_normal4((uint32_t)rid_glob, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z4);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 if (l == 0) zpre0[e] = z4[e];
@@ -612,7 +723,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             if (l == 1 && scorer && t > a.t0 && defer_score) score(t - 1);
             // fused CEM: next step's actions are drawn here by the row's sampler thread (third action buffer)
             if (CEMF && l == (L > 1 ? 1 : 0) && sampler && more)
-              cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, seq_n, t + 1,
+              cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, a.seq0 + seq_n, t + 1,
                                  m.A, act_buf(t + 1), pop_row);
           } else if (l == 2 && owner && !cem) {
             if (!more) continue;
@@ -637,6 +748,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         }
 
         // ---- output layer: groups of 4 outputs; Gaussian sample, delta add-back (branch-free inner maths) ----
+        const uint32_t t_out = t_lane + ((KR && (g & 1u)) ? kAcc1 : 0u);  // KR: the output layer's accumulator is g & 1
         mbar_wait(&bar_acc[0], acc0_par);
         acc0_par ^= 1u;
         ++g;
@@ -644,8 +756,8 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         if (stamp) a.timeline[sp++] = clock64();  // output accumulator ready
         for (int gq = CS - 1 - cs; gq < ngroups; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
           uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
-          tmem_ld4(t_lane + (uint32_t)(4 * gq), rm);
-          if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rl);
+          tmem_ld4(t_out + (uint32_t)(4 * gq), rm);
+          if (!m.deterministic) tmem_ld4(t_out + (uint32_t)(m.outp + 4 * gq), rl);
           tmem_ld_wait();
           const int u = (gq - (CS - 1 - cs)) / CS;
           if (stamp) a.timeline[40 + 4 * u] = clock64();
@@ -662,14 +774,14 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
 #pragma unroll
               for (int e = 0; e < 4; ++e) z[e] = u == 0 ? zpre0[e] : zpre1[e];
             } else {
-              philox_normal4((uint32_t)rid, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z);
+              philox_normal4((uint32_t)rid_glob, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z);
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int oc = min(4 * gq + e, m.out - 1);
               const float e1 = __expf(c_maxlv[oc] - __uint_as_float(rl[e]));        // exp(max - lv)   (inf is fine)
               const float e2 = __fdividef(c_ratio[oc], 1.f + e1);                  // exp(max - min) / (1 + e1)
-              const float sd = c_sdmin[oc] * sqrtf(1.f + e2);                      // sqrt(exp(clamped logvar))
+              const float sd = c_sdmin[oc] * sqrt_approx(1.f + e2);                // sqrt(exp(clamped logvar))
               pred[e] = fmaf(sd, z[e], __uint_as_float(rm[e]));
             }
           } else {
@@ -952,14 +1064,15 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int k, int
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-static int g_sm_count = 0, g_max_smem = 0;
+static int g_sm_count = 0, g_max_smem = 0, g_limits_dev = -1;
 
-static int tc_device_limits() {
-  if (g_sm_count) return B200PETS_OK;
+static int tc_device_limits() {  // cached per device (a process may drive several)
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
+  if (dev == g_limits_dev) return B200PETS_OK;
   CUDA_TRY(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  g_limits_dev = dev;
   return B200PETS_OK;
 }
 
@@ -990,8 +1103,16 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   p.off_act = off; off += 3u * (uint32_t)kTileM * p.act_ld * 4;
   p.off_const = off; off += (uint32_t)(2 * m.in + 3 * m.out + m.D + kTileM + 2 * kCemTabDims) * 4;
   off = (off + 15u) & ~15u;
-  p.off_bar = off; off += (2 * kMaxStages + 4) * 8 + 16;
+  p.off_bar = off; off += (2 * kMaxStages + 4 + 4) * 8 + 16;
   off = (off + 127u) & ~127u;
+  // K-round pipeline: every padded width must fit one of two 208-column accumulators, the A operand 96 TMEM columns
+  // (+ one shared-memory K step), and the layer-0 operand must not need the shared-memory tile
+  p.kr = 1;
+  for (int l = 0; l < p.nlayers; ++l)
+    if (m.Np[l] > (int)kAcc1 || m.Kp[l] > 16 * (kTmemKSteps + 1)) p.kr = 0;
+  if (m.Kp[0] > 16 * kTmemKSteps) p.kr = 0;
+  p.off_atail = off;
+  if (p.kr) off += (uint32_t)kTileM * 16u * 2u;
   p.off_ring = off;
   int S = ((int)max_smem - (int)off) / (int)p.stage_bytes;
   if (S < 1) return false;  // S >= 2: one layer in use, the next one in flight; S == 1 (wide layers): no prefetch
@@ -1018,7 +1139,7 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
                               m.in, m.hid, m.out);
   long long tiles;
   if (a.slot_mode >= 1) {
-    tiles = (a.B + kTileM - 1) / kTileM;
+    tiles = (long long)a.P * shuffle_geom(a.seq0, a.N, a.n_glob).C_loc;
   } else {
     long long Bm = a.B / m.M;
     tiles = (long long)m.M * ((Bm + kTileM - 1) / kTileM);
@@ -1026,18 +1147,17 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
   const unsigned grid = (unsigned)min((long long)g_sm_count, tiles);
   const bool cemf = a.cem_mu != nullptr || a.tail_counter != nullptr;
   void (*kern)(const ModelDev, const RolloutArgs, const TcPlan, const long long) = nullptr;
+  static const bool kr_off = [] { const char* e = getenv("B200PETS_TC_KR"); return e && e[0] == '0'; }();  // A/B switch
+  const bool kr = p.kr && !kr_off;
+#define B200PETS_PICK(ACTV)                                                                                              \
+  kern = cemf ? (kr ? rollout_tc_kernel<ACTV, kEpiSplit, true, true> : rollout_tc_kernel<ACTV, kEpiSplit, true, false>)   \
+              : (kr ? rollout_tc_kernel<ACTV, kEpiSplit, false, true> : rollout_tc_kernel<ACTV, kEpiSplit, false, false>)
   switch (m.act) {
-    case B200PETS_ACT_SILU:
-      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, true> : rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, false>;
-      break;
-    case B200PETS_ACT_RELU:
-      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, true> : rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, false>;
-      break;
-    default:
-      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, true>
-                  : rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, false>;
-      break;
+    case B200PETS_ACT_SILU: B200PETS_PICK(B200PETS_ACT_SILU); break;
+    case B200PETS_ACT_RELU: B200PETS_PICK(B200PETS_ACT_RELU); break;
+    default: B200PETS_PICK(B200PETS_ACT_LEAKY_RELU); break;
   }
+#undef B200PETS_PICK
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
   kern<<<grid, 64 + 128 * kEpiSplit, p.smem_bytes, stream>>>(m, a, p, tiles);
   CUDA_TRY(cudaGetLastError());

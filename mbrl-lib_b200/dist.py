@@ -1,8 +1,15 @@
 """Population-sharded CEM across GPUs: one process per GPU, weights / normaliser /
-observation / (mu, sigma) replicated, every rank evaluates its own slice of the population, and the only
-exchange per CEM iteration is ONE all-gather of each rank's local top-k records ``[value, sequence]``
+observation / (mu, sigma) replicated, every rank evaluates its own contiguous slice of the GLOBAL population, and
+the only exchange per CEM iteration is ONE all-gather of each rank's local top-k records ``[value, sequence]``
 (NCCL over NVLink / NVSwitch; <= 290 KB at config 2 on 8 GPUs, latency bound).  Every rank then refits from
 the identical gathered records, so (mu, sigma, best) stay bit-identical on all ranks without a broadcast.
+
+Results do not depend on the number of GPUs: the population noise is keyed by global sequence index
+(``b200pets_cem_sample_shard``), the model noise by global row id and the TS1 member draw by global shuffle group
+(``b200pets_rollout_cfg.first_sequence / global_population``), records arrive in global index order (contiguous
+shards, rank-major gather) and the refit sums the elites in that order.  ``tests/test_gpu_parity.py`` checks that
+two shards evaluated one after the other on one GPU reproduce the unsharded plan bit for bit, and
+``tests/test_gpu_multi.py`` does the same across two processes with NCCL.
 
 The reference has no multi-GPU path; semantics are those of ``CEMOptimizer.optimize``
 (mbrl/planning/trajectory_opt.py:142-188) over the union population.
@@ -45,11 +52,15 @@ def gather_records(local_records: torch.Tensor, group=None) -> torch.Tensor:
 class ShardedCEMOptimizer:
     """CEM whose population of ``population_size`` (global) is split over the ranks of ``group``.
 
-    ``population_size`` / ``elite_ratio`` keep their reference meaning for the *global* population."""
+    ``population_size`` / ``elite_ratio`` keep their reference meaning for the *global* population.
+    ``rank`` / ``world`` / ``gather`` default to the process group's; tests pass them explicitly to run several
+    shards in one process (``gather`` maps this rank's ``[k, 1 + dims]`` records to the ``[world * k, 1 + dims]``
+    union in rank order)."""
 
     def __init__(self, num_iterations: int, elite_ratio: float, population_size: int,
                  lower_bound: Sequence[Sequence[float]], upper_bound: Sequence[Sequence[float]], alpha: float, device,
-                 return_mean_elites: bool = False, group=None):
+                 return_mean_elites: bool = False, group=None, *, rank: Optional[int] = None, world: Optional[int] = None,
+                 gather: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
         self.num_iterations = num_iterations
         self.population_size = population_size
         self.elite_num = int(np.ceil(population_size * elite_ratio).astype(np.int32))
@@ -57,7 +68,9 @@ class ShardedCEMOptimizer:
         self.return_mean_elites = return_mean_elites
         self.device = torch.device(device)
         self.group = group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self._gather = gather if gather is not None else (lambda rec: gather_records(rec, self.group))
         lo, hi = shard_bounds(population_size, self.rank, self.world)
         self.local_population = hi - lo
         self.local_offset = lo
@@ -73,6 +86,28 @@ class ShardedCEMOptimizer:
         self.lib = _lib.load()
         self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self._offset = 0
+        self._buf = None
+        self.record_values = False
+        self.last_values = None
+        self.comm_events = None  # set to [] to record (start, end) CUDA events around every collective
+
+    def _buffers(self, shape):
+        dims = int(np.prod(shape))
+        key = (tuple(shape), self.local_population)
+        if self._buf is None or self._buf["key"] != key:
+            dev, n_loc, k = self.device, self.local_population, self.k_local
+            nbytes = max(self.lib.b200pets_cem_update_workspace_bytes(n_loc, dims, k),
+                         self.lib.b200pets_cem_update_workspace_bytes(k * self.world, dims, self.elite_num))
+            self._buf = {
+                "key": key,
+                "mu": torch.empty(dims, device=dev), "disp": torch.empty(dims, device=dev),
+                "best_val": torch.empty(1, device=dev), "best_sol": torch.empty(dims, device=dev),
+                "pop": torch.empty((n_loc,) + tuple(shape), device=dev),
+                "records": torch.empty(k, 1 + dims, device=dev),
+                "values": torch.empty(n_loc, dtype=torch.float32, device=dev),
+                "ws": torch.empty(nbytes, dtype=torch.uint8, device=dev),
+            }
+        return self._buf
 
     def optimize(self, obj_fun: Callable[[torch.Tensor], torch.Tensor], x0: torch.Tensor,
                  callback: Optional[Callable] = None) -> torch.Tensor:
@@ -81,39 +116,44 @@ class ShardedCEMOptimizer:
         shape = tuple(x0.shape)
         dims = int(np.prod(shape))
         n_loc, k = self.local_population, self.k_local
-        mu = x0.reshape(-1).clone()
-        disp = (((self.upper_bound - self.lower_bound) ** 2) / 16).reshape(-1).clone()
-        best_val = torch.full((1,), float("-inf"), device=dev)
-        best_sol = torch.empty(dims, device=dev)
-        pop = torch.empty((n_loc,) + shape, device=dev)
-        records = torch.empty(k, 1 + dims, device=dev)
-        nbytes = max(self.lib.b200pets_cem_update_workspace_bytes(n_loc, dims, k),
-                     self.lib.b200pets_cem_update_workspace_bytes(k * self.world, dims, self.elite_num))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        b = self._buffers(shape)
+        mu, disp, best_val, best_sol, pop, records, ws = (b["mu"], b["disp"], b["best_val"], b["best_sol"], b["pop"],
+                                                          b["records"], b["ws"])
+        mu.copy_(x0.reshape(-1))
+        disp.copy_((((self.upper_bound - self.lower_bound) ** 2) / 16).reshape(-1))
+        best_val.fill_(float("-inf"))
+        nbytes = ws.numel()
         self._offset += 1
-        stream = _lib.stream_ptr()
         from .planning import _FusedObjective
 
         fused = obj_fun if isinstance(obj_fun, _FusedObjective) and obj_fun.model_env.ts1 == "tile_shuffle" else None
+        values = b["values"]
+        if self.record_values:
+            self.last_values = torch.empty(self.num_iterations, n_loc, device=dev)
         if fused is not None:
             env = fused.model_env
             env.staged.ensure_fresh()
             prop = env._propagation()
             H = shape[0]
+            # the same (seed, offset) on every rank: draws are keyed by GLOBAL sequence / row / group indices
+            call = env._next_offset()
             rcfg = _lib.RolloutCfg(n_loc, H, fused.num_particles, _lib.PREC[env.precision], _lib.PROP[prop],
-                                   _lib.TS1_TILE_SHUFFLE, (env._seed + 0x9E3779B97F4A7C15 * self.rank) & 0xFFFFFFFFFFFFFFFF, 0)
+                                   _lib.TS1_TILE_SHUFFLE, env._seed, 0, self.local_offset, self.population_size)
             obs0 = env._obs_to_device(fused.obs)
-            values = torch.empty(n_loc, dtype=torch.float32, device=dev)
             eval_ws = env._workspace(self.lib.b200pets_eval_workspace_bytes(env.staged.handle, C.byref(rcfg)))
+            seed = env._seed
+        else:
+            call = self._offset
+            seed = self._seed
         with torch.cuda.device(dev):
+            stream = _lib.stream_ptr()
             for i in range(self.num_iterations):
-                # rank-distinct Philox stream: offset encodes (call, iteration, rank)
-                off = (self._offset * 1024 + i) * 64 + self.rank
-                _lib.check(self.lib.b200pets_cem_sample(n_loc, dims, _lib.ptr(mu), _lib.ptr(disp), _lib.ptr(self.lower_bound),
-                                                        _lib.ptr(self.upper_bound), None, self._seed, off, 0, _lib.ptr(pop),
-                                                        stream), "cem_sample")
+                off = call * 1024 + i
+                _lib.check(self.lib.b200pets_cem_sample_shard(
+                    n_loc, self.local_offset, dims, _lib.ptr(mu), _lib.ptr(disp), _lib.ptr(self.lower_bound),
+                    _lib.ptr(self.upper_bound), None, seed, off, 0, _lib.ptr(pop), stream), "cem_sample_shard")
                 if fused is not None:  # ModelEnv objective: one C call, no per-iteration host staging
-                    rcfg.offset = env._next_offset()
+                    rcfg.offset = off
                     _lib.check(self.lib.b200pets_eval_sequences(env.staged.handle, C.byref(rcfg), _lib.ptr(obs0), _lib.ptr(pop), None,
                                                                 None, _lib.ptr(values), None, _lib.ptr(eval_ws), eval_ws.numel(),
                                                                 stream), "eval_sequences")
@@ -121,9 +161,17 @@ class ShardedCEMOptimizer:
                     values = obj_fun(pop).to(dev, torch.float32).contiguous()
                 if callback is not None:
                     callback(pop, values, i)
+                if self.record_values:
+                    self.last_values[i].copy_(values)
                 _lib.check(self.lib.b200pets_cem_local_topk(n_loc, dims, k, _lib.ptr(pop), _lib.ptr(values), _lib.ptr(records),
                                                             _lib.ptr(ws), nbytes, stream), "cem_local_topk")
-                allrec = gather_records(records, self.group)  # <- the single collective of this iteration
+                if self.comm_events is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                allrec = self._gather(records)  # <- the single collective of this iteration
+                if self.comm_events is not None:
+                    e1.record()
+                    self.comm_events.append((e0, e1))
                 _lib.check(self.lib.b200pets_cem_update_from_records(
                     allrec.shape[0], dims, self.elite_num, float(self.alpha), 1, 0, _lib.ptr(allrec), _lib.ptr(mu),
                     _lib.ptr(disp), _lib.ptr(best_val), _lib.ptr(best_sol), None, _lib.ptr(ws), nbytes, stream),

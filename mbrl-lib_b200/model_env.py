@@ -53,8 +53,21 @@ class ModelEnv:
         return pm
 
     def _next_offset(self) -> int:
+        """Philox stream counter of this environment: one value per API call.  ``b200pets_cem_plan`` derives the
+        offsets of its iterations as ``counter * 1024 + it``; single evaluations / steps use ``counter * 1024``
+        (:meth:`_call_offset`), so the two kinds of call never share a stream."""
         self._offset += 1
         return self._offset
+
+    def _call_offset(self) -> int:
+        return self._next_offset() * 1024
+
+    def _few_groups(self, population: int, particles: int) -> bool:
+        """Tile shuffle deals members to groups of 128 rows; with fewer groups than twice the members the draw would
+        collapse to (almost) one member for everybody, so such small batches use generated permutations instead
+        (exact reference rule, gaussian_mlp.py:202-212)."""
+        groups = particles * ((population + 127) // 128)
+        return groups < 2 * len(self.staged.members())
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
@@ -67,13 +80,43 @@ class ModelEnv:
         if self._obs_pin is None or self._obs_pin.numel() != D:
             self._obs_pin = torch.empty(D, dtype=torch.float32).pin_memory()
             self._obs_dev = torch.empty(D, dtype=torch.float32, device=self.device)
-            self._obs_evt = torch.cuda.Event()
+            with torch.cuda.device(self.device):
+                self._obs_evt = torch.cuda.Event()
         else:
             self._obs_evt.synchronize()  # the previous async H2D copy must have read the pinned buffer before we overwrite it
         self._obs_pin.copy_(torch.from_numpy(np.ascontiguousarray(initial_state, dtype=np.float32)))
-        self._obs_dev.copy_(self._obs_pin, non_blocking=True)
-        self._obs_evt.record()
+        with torch.cuda.device(self.device):  # copy and event on the model's device / stream, whatever the current one is
+            self._obs_dev.copy_(self._obs_pin, non_blocking=True)
+            self._obs_evt.record()
         return self._obs_dev
+
+    def shuffle_member_assignment(self, population: int, horizon: int, num_particles: int, offset: int,
+                                  first_sequence: int = 0, global_population: int = 0) -> torch.Tensor:
+        """Row -> member map ``[H, B]`` (positions in the elite list, rows ``r = n * P + p`` of this shard) that the
+        kernels use in tile-shuffle mode for Philox ``offset`` (``b200pets_shuffle_member_map``).  Diagnostics /
+        parity tests: the oracle consumes it as the reference's per-step assignment (gaussian_mlp.py:202-212)."""
+        prop = self._propagation()
+        cfg = _lib.RolloutCfg(population, horizon, num_particles, _lib.PREC[self.precision], _lib.PROP[prop],
+                              _lib.TS1_TILE_SHUFFLE, self._seed, offset, first_sequence, global_population)
+        groups = int(self.lib.b200pets_shuffle_num_groups(C.byref(cfg)))
+        M = len(self.staged.members())
+        gm = torch.empty(horizon, groups, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200pets_shuffle_member_map(C.byref(cfg), M, _lib.ptr(gm), _lib.stream_ptr()),
+                       "shuffle_member_map")
+        gm = gm.cpu().numpy()
+        c_lo = first_sequence // 128
+        C_loc = (first_sequence + population - 1) // 128 - c_lo + 1
+        assert groups == num_particles * C_loc
+        assign = np.full((horizon, population * num_particles), -1, dtype=np.int64)
+        for p in range(num_particles):
+            for ci in range(C_loc):
+                lo = max((c_lo + ci) * 128, first_sequence) - first_sequence
+                hi = min((c_lo + ci + 1) * 128, first_sequence + population) - first_sequence
+                rows = np.arange(lo, hi) * num_particles + p
+                assign[:, rows] = gm[:, p * C_loc + ci][:, None]
+        assert (assign >= 0).all()
+        return torch.from_numpy(assign)
 
     # ---- reference API ---------------------------------------------------------------------------------
     def reset(self, initial_obs_batch: np.ndarray, return_as_np: bool = True) -> Dict[str, torch.Tensor]:
@@ -91,7 +134,7 @@ class ModelEnv:
         return state
 
     def step(self, actions, model_state: Dict[str, torch.Tensor], sample: bool = False, *,
-             _perm: Optional[torch.Tensor] = None, _eps: Optional[torch.Tensor] = None):
+             _perm: Optional[torch.Tensor] = None, _eps: Optional[torch.Tensor] = None, _offset: Optional[int] = None):
         assert len(actions.shape) == 2  # batch, action_dim  (model_env.py:108)
         self.staged.ensure_fresh()
         with torch.no_grad():
@@ -110,7 +153,7 @@ class ModelEnv:
                     perm = model_state.get("propagation_indices")
                     if perm is None:
                         raise ValueError("When using propagation='fixed_model', `propagation_indices` must be provided.")
-                elif prop == "random_model" and self.ts1 == "perms":
+                elif prop == "random_model" and (self.ts1 == "perms" or self._few_groups(B, 1)):
                     perm = torch.randperm(B, device=self.device)
             if perm is not None:
                 perm = perm.to(torch.int64).contiguous()
@@ -121,7 +164,8 @@ class ModelEnv:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.b200pets_step(
                     self.staged.handle, _lib.PREC[self.precision], _lib.PROP[prop], B, _lib.ptr(obs), _lib.ptr(actions),
-                    _lib.ptr(perm), _lib.ptr(_eps), self._seed, self._next_offset(), int(bool(sample)), _lib.ptr(next_obs),
+                    _lib.ptr(perm), _lib.ptr(_eps), self._seed, self._call_offset() if _offset is None else _offset,
+                    int(bool(sample)), _lib.ptr(next_obs),
                     _lib.ptr(reward), _lib.ptr(done), _lib.stream_ptr()), "step")
             rewards = reward.view(-1, 1)
             dones = done.view(-1, 1).bool()
@@ -140,7 +184,8 @@ class ModelEnv:
 
     def evaluate_action_sequences(self, action_sequences: torch.Tensor, initial_state: np.ndarray, num_particles: int, *,
                                   _perms: Optional[torch.Tensor] = None, _eps: Optional[torch.Tensor] = None,
-                                  _row_returns: Optional[torch.Tensor] = None) -> torch.Tensor:
+                                  _row_returns: Optional[torch.Tensor] = None, _offset: Optional[int] = None,
+                                  _shard=(0, 0)) -> torch.Tensor:
         with torch.no_grad():
             assert len(action_sequences.shape) == 3  # model_env.py:166
             population_size, horizon, action_dim = action_sequences.shape
@@ -161,13 +206,13 @@ class ModelEnv:
                     if B % M != 0:
                         raise ValueError("To use GaussianMLP's ensemble propagation, the batch size must "
                                          "be a multiple of the number of models in the ensemble.")
-                    if self.ts1 == "perms":
+                    if self.ts1 == "perms" or self._few_groups(population_size, num_particles):
                         perms = torch.randperm(B, device=self.device).view(1, B)
-                elif prop == "random_model" and self.ts1 == "perms":
+                elif prop == "random_model" and (self.ts1 == "perms" or self._few_groups(population_size, num_particles)):
                     perms = torch.stack([torch.randperm(B, device=self.device) for _ in range(horizon)])
             cfg = _lib.RolloutCfg(population_size, horizon, num_particles, _lib.PREC[self.precision], _lib.PROP[prop],
                                   _lib.TS1_PERMS if perms is not None else _lib.TS1_TILE_SHUFFLE, self._seed,
-                                  self._next_offset())
+                                  self._call_offset() if _offset is None else _offset, int(_shard[0]), int(_shard[1]))
             obs0 = self._obs_to_device(initial_state)
             returns = torch.empty(population_size, dtype=torch.float32, device=self.device)
             need = self.lib.b200pets_eval_workspace_bytes(self.staged.handle, C.byref(cfg))

@@ -116,9 +116,9 @@ class CEMOptimizer(Optimizer):
         else:
             disp.copy_((((self.upper_bound - self.lower_bound) ** 2) / 16).reshape(-1))
         b["best_val"].fill_(float("-inf"))
-        stream = _lib.stream_ptr()
         base = _next_seed_offset(self) * 1024
         with torch.cuda.device(self.device):
+            stream = _lib.stream_ptr()
             for i in range(self.num_iterations):
                 z = None if _noise is None else _noise[i].to(self.device, torch.float32).contiguous()
                 _lib.check(self.lib.b200pets_cem_sample(
@@ -144,7 +144,8 @@ class CEMOptimizer(Optimizer):
         perms = eps = None
         if model_noise is not None:
             perms, eps = model_noise
-        if perms is None and prop in ("random_model", "fixed_model") and env.ts1 == "perms":
+        if perms is None and prop in ("random_model", "fixed_model") and (
+                env.ts1 == "perms" or env._few_groups(self.population_size, obj.num_particles)):
             B = self.population_size * obj.num_particles
             n = H if prop == "random_model" else 1
             perms = torch.stack([torch.stack([torch.randperm(B, device=self.device) for _ in range(n)])
@@ -224,16 +225,19 @@ class ICEMOptimizer(Optimizer):
         var = self.initial_var.reshape(-1).clone()
         best_val = torch.full((1,), float("-inf"), device=dev)
         best_sol = torch.empty(dims, device=dev)
-        stream = _lib.stream_ptr()
         base = _next_seed_offset(self) * 1024
         sizes = self.population_sizes()
         elites_new = torch.empty(self.elite_num, H, A, device=dev)
         with torch.cuda.device(dev):
+            stream = _lib.stream_ptr()
             for i in range(self.num_iterations):
                 n = sizes[i]
                 extra = 0
+                # the reference indexes `randperm(elite_num)[:keep_elite_size]`: when population_size_module rounds
+                # keep_elite_size above elite_num only elite_num rows exist (trajectory_opt.py:443-447)
+                keep = min(self.keep_elite_size, self.elite_num)
                 if self.elite is not None:
-                    extra = 1 if (i == self.num_iterations - 1 and i != 0) else self.keep_elite_size
+                    extra = 1 if (i == self.num_iterations - 1 and i != 0) else keep
                 pop = torch.empty(n + extra, H, A, device=dev)
                 nz = _noise[i] if _noise is not None else {}
                 sr = nz.get("sr")
@@ -249,9 +253,9 @@ class ICEMOptimizer(Optimizer):
                         idx = nz.get("keep_perm")
                         if idx is None:
                             idx = torch.randperm(self.elite_num, device=dev)
-                        idx = idx[: self.keep_elite_size].to(torch.int64).contiguous()
+                        idx = idx[:keep].to(torch.int64).contiguous()
                         _lib.check(self.lib.b200pets_icem_append_elites(
-                            self.keep_elite_size, H, A, _lib.ptr(self.elite), _lib.ptr(idx), int(i == 0), _lib.ptr(mu),
+                            keep, H, A, _lib.ptr(self.elite), _lib.ptr(idx), int(i == 0), _lib.ptr(mu),
                             _lib.ptr(var), _lib.ptr(nz.get("end_eps")), self._seed, base + i, _lib.ptr(pop[n:]), stream),
                             "icem_append_elites")
                 values = obj_fun(pop)
@@ -300,9 +304,9 @@ class MPPIOptimizer(Optimizer):
         pop = torch.empty(N, H, A, device=dev)
         nbytes = self.lib.b200pets_mppi_update_workspace_bytes(N, H * A)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        stream = _lib.stream_ptr()
         base = _next_seed_offset(self) * 1024
         with torch.cuda.device(dev):
+            stream = _lib.stream_ptr()
             for k in range(self.refinements):
                 z = None if _noise is None else _noise[k].to(dev, torch.float32).contiguous()
                 _lib.check(self.lib.b200pets_mppi_sample(N, H, A, float(self.beta), _lib.ptr(self.mean), _lib.ptr(past_action),

@@ -134,6 +134,13 @@ _register(CaseSpec("walker_ant", obs_dim=17, act_dim=6, hid_size=72, num_layers=
                    population=20, horizon=8, particles=4, obs0_first=1.2))
 
 
+# learned reward column AND a named reward_fn (the explicit fn wins, model_env.py:124-128), ant termination
+_register(CaseSpec("ant_learned_fn", obs_dim=27, act_dim=8, hid_size=64, num_layers=2, ensemble_size=3,
+                   elites=None, activation="silu", propagation="random_model", normalize="float64",
+                   learned_rewards=True, reward_fn="halfcheetah", term_fn="ant",
+                   population=24, horizon=7, particles=5, obs0_first=0.6))
+
+
 def _rng(spec: CaseSpec, stream: int) -> np.random.Generator:
     return np.random.default_rng([spec.seed, stream, int(hashlib.sha1(spec.name.encode()).hexdigest()[:8], 16)])
 

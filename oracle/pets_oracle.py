@@ -188,12 +188,41 @@ class OracleModel:
             x = ((x - self.norm_mean) / self.norm_std).float()
         return x
 
-    def forward_propagated(self, x: torch.Tensor, perm: Optional[torch.Tensor]):
+    def forward_assigned(self, x: torch.Tensor, assign: torch.Tensor):
+        """gaussian_mlp.py:202-212 with the row -> member map given directly instead of through a permutation
+        (``assign[r]`` = position in the elite list of the member row r uses).  This is what the reference computes
+        for ANY permutation that induces this map; the CUDA path's in-kernel "tile shuffle" exports its map
+        (b200pets_shuffle_member_map) and is checked against this function."""
+        B = x.shape[0]
+        M = len(self.members)
+        mean_out = None
+        lv_out = None
+        for mpos in range(M):
+            rows = torch.nonzero(assign == mpos).view(-1)
+            if rows.numel() == 0:
+                continue
+            keep = self.members
+            self.members = [keep[mpos]]
+            try:
+                mean, lv = self.mlp(x[rows].unsqueeze(0))
+            finally:
+                self.members = keep
+            if mean_out is None:
+                mean_out = torch.empty(B, mean.shape[-1])
+                lv_out = torch.empty(B, lv.shape[-1]) if lv is not None else None
+            mean_out[rows] = mean[0]
+            if lv is not None:
+                lv_out[rows] = lv[0]
+        return mean_out, lv_out
+
+    def forward_propagated(self, x: torch.Tensor, perm: Optional[torch.Tensor], assign: Optional[torch.Tensor] = None):
         """gaussian_mlp.py:156-216: shuffle rows to members, run, un-shuffle (or member average)."""
         B = x.shape[0]
         M = len(self.members)
         if B % M != 0:
             raise ValueError(f"batch {B} not a multiple of {M} models")  # gaussian_mlp.py:195-200
+        if assign is not None and self.spec.propagation != "expectation":
+            return self.forward_assigned(x, assign)
         if self.spec.propagation == "expectation":
             mean, lv = self.mlp(x.unsqueeze(0))
             return mean.mean(dim=0), (lv.mean(dim=0) if lv is not None else None)
@@ -209,12 +238,12 @@ class OracleModel:
             out_lv[perm] = lv
         return out_mean, out_lv
 
-    def step(self, obs, act, perm, eps, sample=True):
+    def step(self, obs, act, perm, eps, sample=True, assign=None):
         """ModelEnv.step (model_env.py:87-140) over OneDTransitionRewardModel.sample (one_dim_tr_model.py
         :245-289) and Ensemble.sample_1d (model.py:426-473).  Returns next_obs, reward[B,1], done[B,1]."""
         sp = self.spec
         x = self.model_input(obs, act)
-        mean, lv = self.forward_propagated(x, perm)
+        mean, lv = self.forward_propagated(x, perm, assign)
         if sp.deterministic or not sample:
             preds = mean
         else:
@@ -226,12 +255,15 @@ class OracleModel:
             for d in sp.no_delta_list:
                 tmp[:, d] = nobs[:, d]
             nobs = tmp
-        rew = preds[:, -1:] if sp.learned_rewards else REWARD_FNS[sp.reward_fn](act, nobs)
+        # model_env.py:124-128: `pred_rewards if self.reward_fn is None else self.reward_fn(...)`: an explicit
+        # reward_fn wins even when the model also learns a reward column
+        rew = REWARD_FNS[sp.reward_fn](act, nobs) if sp.reward_fn else preds[:, -1:]
         done = TERM_FNS[sp.term_fn](act, nobs)
         return nobs, rew, done
 
-    def evaluate_action_sequences(self, actions, obs0, particles, perms, eps, return_rows=False):
-        """model_env.py:145-191.  actions [N,H,A] f32; obs0 [D]; perms [H or 1, B]; eps [H,B,out]."""
+    def evaluate_action_sequences(self, actions, obs0, particles, perms, eps, return_rows=False, assign=None):
+        """model_env.py:145-191.  actions [N,H,A] f32; obs0 [D]; perms [H or 1, B]; eps [H,B,out];
+        assign [H or 1, B] optional row -> member map used instead of perms (see forward_assigned)."""
         N, H, _ = actions.shape
         P = particles
         B = N * P
@@ -241,10 +273,14 @@ class OracleModel:
         for t in range(H):
             a = torch.repeat_interleave(actions[:, t, :], P, dim=0)
             perm = None
-            if self.spec.propagation != "expectation":
+            if self.spec.propagation != "expectation" and assign is None:
                 perm = perms[0] if self.spec.propagation == "fixed_model" else perms[t]
             e = eps[t] if eps is not None else None
-            obs, rew, done = self.step(obs, a, perm, e, sample=True)
+            asg = None
+            if assign is not None:
+                asg = assign[0] if assign.shape[0] == 1 else assign[t]
+                perm = None
+            obs, rew, done = self.step(obs, a, perm, e, sample=True, assign=asg)
             rew = rew.clone()
             rew[dead] = 0
             dead |= done

@@ -1,0 +1,269 @@
+"""Exact parity of the PRODUCTION TS1 mode (in-kernel "tile shuffle", the mode bench.py times) against the oracle.
+
+The kernels export the member every shuffle group uses at every step (b200pets_shuffle_member_map); the oracle
+consumes it as the reference's row -> member assignment (gaussian_mlp.py:202-212 with the permutation replaced by
+the map it induces, ``OracleModel.forward_assigned``, itself pinned to the golden-pinned permutation path by
+tests/test_oracle_golden.py).  Model noise is injected, so the comparison is at the same bars as the explicit-
+permutation tests: 2e-4 (fp32 kernel) / 5e-3 against the bf16-operand oracle (tensor-core kernel), at BASELINE
+config 2's FULL size (pop 500 x 20 particles x 30 steps), for one evaluation and for the fused CEM plan
+(b200pets_cem_plan: the call bench.py's `value` times).
+
+Also here: shard invariance (the property that makes multi-GPU results independent of the number of GPUs), the
+distribution-level equivalence of the tile-shuffle law and the reference's randperm law (two-sample KS over 200
+draws each), and ShardedCEMOptimizer == CEMOptimizer on the union population (two shards on one GPU).
+"""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from mbrl_lib_b200 import synthetic as syn
+from test_gpu_parity import DEV, assert_close_continuous, assert_close_discrete, make_env
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(spec, arrays, bf16):
+    from oracle import pets_oracle as po
+
+    m = po.OracleModel(spec, arrays)
+    m.emulate_bf16 = bf16
+    return m
+
+
+def _eval_shuffle(env, spec, inp, offset, shard=(0, 0), rows=False, eps=None, actions=None):
+    acts = torch.from_numpy(inp["actions"] if actions is None else actions).to(DEV)
+    e = None if spec.deterministic else torch.from_numpy(inp["eps"] if eps is None else eps).to(DEV)
+    rr = torch.empty(acts.shape[0] * spec.particles, device=DEV) if rows else None
+    out = env.evaluate_action_sequences(acts, inp["obs0"], spec.particles, _eps=e, _row_returns=rr, _offset=offset,
+                                        _shard=shard)
+    torch.cuda.synchronize()
+    return (rr if rows else out).cpu().numpy()
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 2e-4), ("bf16_tc", 5e-3)])
+@pytest.mark.parametrize("name", ["halfcheetah", "pets_halfcheetah_small", "humanoid_trunc", "tc_hid64", "cartpole_pets"])
+def test_tile_shuffle_matches_oracle(name, precision, tol):
+    spec, arrays, env = make_env(name, precision, ts1="tile_shuffle")
+    env._few_groups = lambda *a: False  # always the in-kernel draw, also for the small parity cases
+    inp = syn.make_rollout_inputs(spec)
+    offset = 7 * 1024
+    got = _eval_shuffle(env, spec, inp, offset)
+    assign = env.shuffle_member_assignment(spec.population, spec.horizon, spec.particles, offset)
+    M = spec.num_models
+    assert assign.min() >= 0 and assign.max() < M
+    if name == "halfcheetah":  # uniform member draw per (group, step): 80 groups x 30 steps = 2 400 draws over 5 members
+        frac = np.bincount(assign.numpy().reshape(-1), minlength=M) / assign.numel()
+        assert np.abs(frac - 1.0 / M).max() < 0.05, frac
+    ref = _oracle(spec, arrays, precision == "bf16_tc").evaluate_action_sequences(
+        torch.from_numpy(inp["actions"]), inp["obs0"], spec.particles, None, torch.from_numpy(inp["eps"]),
+        assign=assign).numpy()
+    assert_close_continuous(got, ref, tol)
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16_tc"])
+@pytest.mark.parametrize("name", ["cartpole", "hopper_tsinf"])
+def test_tile_shuffle_tsinf_matches_oracle(name, precision):
+    """TSinf without an injected permutation: one member per shuffle group for the whole horizon."""
+    spec, arrays, env = make_env(name, precision, ts1="tile_shuffle")
+    env._few_groups = lambda *a: False
+    inp = syn.make_rollout_inputs(spec)
+    offset = 3 * 1024
+    got = _eval_shuffle(env, spec, inp, offset)
+    assign = env.shuffle_member_assignment(spec.population, spec.horizon, spec.particles, offset)
+    assert bool((assign == assign[:1]).all())  # fixed for the horizon
+    ref = _oracle(spec, arrays, precision == "bf16_tc").evaluate_action_sequences(
+        torch.from_numpy(inp["actions"]), inp["obs0"], spec.particles, None, torch.from_numpy(inp["eps"]),
+        assign=assign[:1]).numpy()
+    if precision == "f32":
+        assert_close_discrete(got, ref, spec.particles)
+    else:  # discrete rewards: a state near a termination threshold may flip a particle at bf16
+        diff = np.abs(got - ref)
+        assert (diff > 1e-2 * np.maximum(1.0, np.abs(ref))).mean() <= 0.05
+        assert abs(got.mean() - ref.mean()) <= 0.02 * max(1.0, abs(ref.mean()))
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16_tc"])
+def test_shard_invariance_bit_exact(precision):
+    """Rows evaluated as shards [0,180) + [180,500) of a global population of 500 (shard boundary inside a shuffle
+    group) equal the unsharded evaluation BIT FOR BIT, with in-kernel Philox noise and member draws: every draw is
+    keyed by global indices."""
+    spec, arrays, env = make_env("halfcheetah", precision, ts1="tile_shuffle")
+    inp = syn.make_rollout_inputs(spec, with_noise=False)
+    N, P = spec.population, spec.particles
+    offset = 11 * 1024
+
+    def run(lo, hi):
+        acts = torch.from_numpy(inp["actions"][lo:hi]).to(DEV)
+        rr = torch.empty((hi - lo) * P, device=DEV)
+        ret = env.evaluate_action_sequences(acts, inp["obs0"], P, _row_returns=rr, _offset=offset, _shard=(lo, N))
+        torch.cuda.synchronize()
+        return ret.cpu().numpy(), rr.cpu().numpy()
+
+    full, full_rows = run(0, N)
+    a, a_rows = run(0, 180)
+    b, b_rows = run(180, N)
+    assert np.array_equal(np.concatenate([a_rows, b_rows]), full_rows)
+    assert np.array_equal(np.concatenate([a, b]), full)
+    assert np.isfinite(full).all() and np.unique(full).size > N // 2
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 5e-4), ("bf16_tc", 5e-3)])
+def test_fused_cem_plan_tile_shuffle_matches_oracle(precision, tol):
+    """b200pets_cem_plan (the call bench.py's `value` times) in its production mode -- tile shuffle -- at config 2's
+    full size, population noise and model noise injected, against the oracle's CEM over the oracle rollout with the
+    exported per-iteration member maps."""
+    import mbrl_lib_b200 as bp
+    from mbrl_lib_b200.planning import _FusedObjective
+    from oracle import pets_oracle as po
+
+    spec, arrays, env = make_env("halfcheetah", precision, ts1="tile_shuffle")
+    inp = syn.make_rollout_inputs(spec, with_noise=False)
+    iters = 2
+    nz = syn.make_cem_noise(spec, iters)
+    H, A, N, P = spec.horizon, spec.act_dim, spec.population, spec.particles
+    lb = np.full((H, A), spec.action_lb).tolist()
+    ub = np.full((H, A), spec.action_ub).tolist()
+    opt = bp.CEMOptimizer(iters, 0.1, N, lb, ub, 0.1, DEV, return_mean_elites=True)
+    opt.record_values = True
+    call = env._offset + 1  # the Philox call counter cem_plan will take
+    sol = opt.optimize(_FusedObjective(env, inp["obs0"], P), x0=torch.zeros(H, A, device=DEV),
+                       _noise=torch.from_numpy(nz["z"]).to(DEV), _model_noise=(None, torch.from_numpy(nz["eps"]).to(DEV)))
+    torch.cuda.synchronize()
+    vals = opt.last_values.cpu().numpy()
+    assigns = [env.shuffle_member_assignment(N, H, P, call * 1024 + it) for it in range(iters)]
+    oracle = _oracle(spec, arrays, precision == "bf16_tc")
+    ref_vals = []
+
+    def obj(pop, i):
+        v = oracle.evaluate_action_sequences(pop, inp["obs0"], P, None, torch.from_numpy(nz["eps"][i]), assign=assigns[i])
+        ref_vals.append(v.numpy())
+        return v
+
+    lbt, ubt = torch.tensor(lb), torch.tensor(ub)
+    ref_sol = po.cem_optimize(obj, torch.zeros(H, A), lbt, ubt, iters, 0.1, N, 0.1, torch.from_numpy(nz["z"]),
+                              return_mean_elites=True)
+    scale = max(1.0, np.abs(ref_vals[0]).max())
+    assert np.abs(vals[0] - ref_vals[0]).max() <= tol * scale  # iteration 0: identical population
+    if precision == "f32":
+        assert np.abs(vals[1] - ref_vals[1]).max() <= tol * scale
+        np.testing.assert_allclose(sol.cpu().numpy(), ref_sol.numpy(), rtol=1e-3, atol=1e-3)
+    else:  # an elite at the selection threshold may flip at bf16: the refit moves by at most 1 of 50 elites
+        assert np.abs(sol.cpu().numpy() - ref_sol.numpy()).max() <= 0.05
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16_tc"])
+def test_mbpo_step_tile_shuffle_full_size_sampled(precision):
+    """config 4 at full size (100 000 start states, sample=True, injected noise), tile-shuffle member draw: a strided
+    subset of rows against the oracle with the exported member of each row."""
+    spec, arrays, env = make_env("mbpo_halfcheetah", precision, ts1="tile_shuffle")
+    B = 100000
+    inp = syn.make_step_inputs(spec, B)
+    state = env.reset(inp["obs"], return_as_np=False)
+    offset = 5 * 1024
+    eps = torch.from_numpy(inp["eps"]).to(DEV)
+    nobs, rew, done, _ = env.step(torch.from_numpy(inp["act"]).to(DEV), state, sample=True, _eps=eps, _offset=offset)
+    torch.cuda.synchronize()
+    assign = env.shuffle_member_assignment(B, 1, 1, offset)[0]
+    frac = np.bincount(assign.numpy(), minlength=spec.num_models) / B  # 782 independent group draws over 5 members
+    assert np.abs(frac - 1.0 / spec.num_models).max() < 0.06, frac
+    rows = np.arange(0, B, 97)
+    oracle = _oracle(spec, arrays, precision == "bf16_tc")
+    on, orw, _ = oracle.step(torch.from_numpy(inp["obs"][rows]), torch.from_numpy(inp["act"][rows]), None,
+                             torch.from_numpy(inp["eps"][rows]), sample=True, assign=assign[rows])
+    tol = 2e-4 if precision == "f32" else 5e-3
+    scale = max(1.0, on.abs().max().item())
+    assert (nobs.cpu()[rows] - on).abs().max().item() <= tol * scale
+    assert (rew.cpu()[rows] - orw).abs().max().item() <= tol * scale
+    assert not bool(done.any())
+
+
+def test_tile_shuffle_law_matches_reference_law_ks():
+    """The tile-shuffle law (an independent uniform member per (shuffle group, step)) against the reference's law
+    (a fresh randperm of all rows per step): per-sequence return distributions over 200 independent draws each,
+    two-sample Kolmogorov-Smirnov per sequence.  Under equality the p-values are uniform: at most 5 % of the
+    sequences may reject at the 1 % level and the mean p-value must sit near 0.5."""
+    from scipy import stats
+
+    spec, arrays, env_perm = make_env("halfcheetah", "bf16_tc", ts1="perms")
+    _, _, env_shuf = make_env("halfcheetah", "bf16_tc", ts1="tile_shuffle")
+    N, H, P, draws = 256, 8, spec.particles, 200
+    inp = syn.make_rollout_inputs(spec, population=N, horizon=H, with_noise=False)
+    acts = torch.from_numpy(inp["actions"]).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    ret_perm = np.empty((draws, N), np.float32)
+    ret_shuf = np.empty((draws, N), np.float32)
+    for d in range(draws):
+        perms = torch.stack([torch.randperm(N * P, device=DEV, generator=g) for _ in range(H)])
+        ret_perm[d] = env_perm.evaluate_action_sequences(acts, inp["obs0"], P, _perms=perms).cpu().numpy()
+        ret_shuf[d] = env_shuf.evaluate_action_sequences(acts, inp["obs0"], P).cpu().numpy()
+    assert np.isfinite(ret_perm).all() and np.isfinite(ret_shuf).all()
+    # the member draw matters for this (untrained, disagreeing) ensemble: across-draw spread is far above noise level
+    assert ret_perm.std(axis=0).mean() > 1e-3
+    pvals = np.array([stats.ks_2samp(ret_perm[:, n], ret_shuf[:, n]).pvalue for n in range(N)])
+    # p-values of neighbouring sequences are correlated (they share draws), hence the slack around uniformity
+    assert (pvals < 0.01).mean() <= 0.08, f"{(pvals < 0.01).mean():.3f} of sequences reject at 1 %"
+    assert 0.3 <= pvals.mean() <= 0.7, pvals.mean()
+    # first two moments of the per-sequence return, pooled over sequences
+    np.testing.assert_allclose(ret_shuf.mean(axis=0), ret_perm.mean(axis=0), atol=5 * ret_perm.std(axis=0).max() / np.sqrt(draws))
+    ratio = ret_shuf.std(axis=0) / ret_perm.std(axis=0)
+    assert 0.9 <= np.median(ratio) <= 1.1, np.median(ratio)
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16_tc"])
+def test_sharded_cem_equals_unsharded_plan(precision):
+    """ShardedCEMOptimizer over two shards (two threads on one GPU, the all-gather replaced by an in-process exchange)
+    produces the plan CEMOptimizer produces on the union population for the same seed: population noise, model noise
+    and member draws are keyed by global indices and the refit sums the elites in global index order."""
+    import mbrl_lib_b200 as bp
+    from mbrl_lib_b200.dist import ShardedCEMOptimizer
+    from mbrl_lib_b200.planning import _FusedObjective
+
+    spec = syn.CASES["halfcheetah"]
+    H, A, N, P = spec.horizon, spec.act_dim, spec.population, spec.particles
+    lb, ub = np.full((H, A), spec.action_lb).tolist(), np.full((H, A), spec.action_ub).tolist()
+    inp = syn.make_rollout_inputs(spec, with_noise=False)
+    iters = 3
+    _, _, env = make_env("halfcheetah", precision, ts1="tile_shuffle")
+    ref_opt = bp.CEMOptimizer(iters, 0.1, N, lb, ub, 0.1, DEV, return_mean_elites=True)
+    ref_opt.record_values = True
+    ref = ref_opt.optimize(_FusedObjective(env, inp["obs0"], P), x0=torch.zeros(H, A, device=DEV)).cpu().numpy()
+    ref_vals = ref_opt.last_values.cpu().numpy()
+
+    world = 2
+    slots = [None] * world
+    barrier = threading.Barrier(world)
+    sols, vals, errs = [None] * world, [None] * world, []
+
+    def worker(rank):
+        try:
+            torch.cuda.set_device(0)
+            _, _, env_r = make_env("halfcheetah", precision, ts1="tile_shuffle")
+
+            def gather(rec):
+                torch.cuda.synchronize()
+                slots[rank] = rec.clone()
+                barrier.wait()
+                out = torch.cat([slots[r] for r in range(world)], dim=0)
+                barrier.wait()
+                return out
+
+            opt = ShardedCEMOptimizer(iters, 0.1, N, lb, ub, 0.1, DEV, return_mean_elites=True, rank=rank, world=world,
+                                      gather=gather)
+            opt.record_values = True
+            sols[rank] = opt.optimize(_FusedObjective(env_r, inp["obs0"], P), x0=torch.zeros(H, A, device=DEV)).cpu().numpy()
+            vals[rank] = opt.last_values.cpu().numpy()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errs, errs
+    assert np.array_equal(sols[0], sols[1])  # every rank holds the same plan without a broadcast
+    assert np.array_equal(np.concatenate([vals[0], vals[1]], axis=1), ref_vals)  # per-sequence returns, every iteration
+    assert np.array_equal(sols[0], ref)

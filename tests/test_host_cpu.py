@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in b200pets.h but not exported by libb200pets.so"
     assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
-    assert lib.b200pets_version() == 1
+    assert lib.b200pets_version() == 2
 
 
 def test_no_cpu_fallback_for_models_on_cpu():

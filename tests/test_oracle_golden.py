@@ -10,7 +10,7 @@ from mbrl_lib_b200 import synthetic as syn
 from oracle import pets_oracle as po
 
 ROLLOUT_CASES = ["cartpole", "halfcheetah", "halfcheetah_small", "pets_halfcheetah_small", "humanoid_trunc",
-                 "relu_expectation", "hopper_tsinf", "cartpole_pets", "pusher_det", "walker_ant", "humanoid_v4", "tc_hid64", "tc_wide", "tc_shallow"]
+                 "relu_expectation", "hopper_tsinf", "cartpole_pets", "pusher_det", "walker_ant", "humanoid_v4", "tc_hid64", "tc_wide", "tc_shallow", "ant_learned_fn"]
 
 
 def _load(golden_dir, name):
@@ -30,6 +30,24 @@ def test_rollout_matches_reference(golden_dir, name):
                                       torch.from_numpy(inp["perms"]), torch.from_numpy(inp["eps"]))
     # same ATen ops as the reference => bit-exact here; 1e-6 leaves room for a different MKL thread split
     np.testing.assert_allclose(ret.numpy(), g["returns"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["halfcheetah_small", "hopper_tsinf", "ant_learned_fn", "tc_hid64"])
+def test_assigned_members_path_equals_permutation_path(name):
+    """``forward_assigned`` (row -> member map given directly; what the GPU tile-shuffle tests feed the oracle) equals the
+    golden-pinned permutation path for the map a permutation induces (gaussian_mlp.py:202-212)."""
+    spec = syn.CASES[name]
+    arrays = syn.make_model_arrays(spec)
+    inp = syn.make_rollout_inputs(spec)
+    m = po.OracleModel(spec, arrays)
+    args = (torch.from_numpy(inp["actions"]), inp["obs0"], spec.particles)
+    ref = m.evaluate_action_sequences(*args, torch.from_numpy(inp["perms"]), torch.from_numpy(inp["eps"])).numpy()
+    B, M = spec.batch, spec.num_models
+    assign = np.empty(inp["perms"].shape, np.int64)
+    for t in range(assign.shape[0]):
+        assign[t, inp["perms"][t]] = np.arange(B) // (B // M)
+    got = m.evaluate_action_sequences(*args, None, torch.from_numpy(inp["eps"]), assign=torch.from_numpy(assign)).numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)  # only the GEMM batch split differs
 
 
 @pytest.mark.parametrize("name,batch", [("mbpo_halfcheetah_small", 1000), ("cartpole", 500)])
