@@ -15,6 +15,10 @@ int launch_rollout_f32(const ModelDev& m, const RolloutArgs& a, cudaStream_t str
 int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stream);
 int launch_umma_selftest(int k, int n, const float* a, const float* b, float* d, cudaStream_t stream);
 int launch_particle_mean(int N, int P, const float* total, float* returns, cudaStream_t stream);
+int launch_cem_update_rows(int population, int dims, int elite_num, float alpha, int unbiased, int use_std,
+                           const float* population_in, const float* row_totals, int particles, float* values, float* mu,
+                           float* dispersion, float* best_value, float* best_solution, void* workspace,
+                           size_t workspace_bytes, void* stream);
 bool tc_supported(const ModelDev& m);
 int launch_umma_bench(int mode, int k, int n, int reps, long long* out, cudaStream_t stream);
 
@@ -301,10 +305,11 @@ size_t b200pets_eval_workspace_bytes(b200pets_model_t model, const b200pets_roll
   return ((B * model->desc.obs_dim * sizeof(float) + 255) & ~(size_t)255) + ((B * sizeof(float) + 255) & ~(size_t)255) + ((B + 255) & ~(size_t)255);
 }
 
-int b200pets_eval_sequences(b200pets_model_t model, const b200pets_rollout_cfg* cfg, const float* obs0,
-                            const float* actions, const int64_t* perms, const float* eps, float* returns,
-                            float* row_returns, void* workspace, size_t workspace_bytes, void* stream_) {
-  if (!model || !cfg || !obs0 || !actions || !returns || !workspace) return b200pets_set_error(B200PETS_EINVAL, "eval_sequences: null argument");
+// the rollout of one evaluation: per-row totals [B] (row r = n * P + p) in *totals_out, no particle mean
+static int eval_rows(b200pets_model_t model, const b200pets_rollout_cfg* cfg, const float* obs0, const float* actions,
+                     const int64_t* perms, const float* eps, float* row_returns, void* workspace, size_t workspace_bytes,
+                     void* stream_, float** totals_out) {
+  if (!model || !cfg || !obs0 || !actions || !workspace) return b200pets_set_error(B200PETS_EINVAL, "eval_sequences: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   const b200pets_model_desc& d = model->desc;
   const int N = cfg->population, H = cfg->horizon, P = cfg->particles;
@@ -364,7 +369,18 @@ int b200pets_eval_sequences(b200pets_model_t model, const b200pets_rollout_cfg* 
     int rc = dispatch(model, precision, a, stream);
     if (rc) return rc;
   }
-  return launch_particle_mean(N, P, total, returns, stream);
+  *totals_out = total;
+  return B200PETS_OK;
+}
+
+int b200pets_eval_sequences(b200pets_model_t model, const b200pets_rollout_cfg* cfg, const float* obs0,
+                            const float* actions, const int64_t* perms, const float* eps, float* returns,
+                            float* row_returns, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!returns) return b200pets_set_error(B200PETS_EINVAL, "eval_sequences: null argument");
+  float* total = nullptr;
+  int rc = eval_rows(model, cfg, obs0, actions, perms, eps, row_returns, workspace, workspace_bytes, stream_, &total);
+  if (rc) return rc;
+  return launch_particle_mean(cfg->population, cfg->particles, total, returns, (cudaStream_t)stream_);  // model_env.py:190-191
 }
 
 int b200pets_step(b200pets_model_t model, int32_t precision, int32_t propagation, int64_t batch, const float* obs,
@@ -450,8 +466,7 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
 
   cem_init_kernel<<<(dims + 255) / 256, 256, 0, stream>>>(dims, x0, lower, upper, ccfg->clipped_normal, mu, disp, best_val);
   CUDA_TRY(cudaGetLastError());
-  // Default: sample -> rollout -> particle mean -> refit (4 small launches per iteration, 1.93 ms per 5-iteration plan
-  // at config 2).  B200PETS_CEM_FUSED=1 selects the fused variants, kept because they are parity-tested but measured
+  // Default: sample -> rollout -> refit (3 launches per iteration; the refit kernel fuses the particle mean).  B200PETS_CEM_FUSED=1 selects the fused variants, kept because they are parity-tested but measured
   // SLOWER on B200: refit by the last CTA of the rollout kernel (2 launches / iteration, 2.01 ms) and, with
   // B200PETS_CEM_SAMPLE_IN_KERNEL=1, the population drawn inside the rollout kernel too (1 launch / iteration,
   // 2.68 ms: every particle row re-derives its sequence's actions on the epilogue's critical path).
@@ -508,14 +523,17 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
     b200pets_rollout_cfg rc_it = *rcfg;
     rc_it.offset = rcfg->offset * 1024 + it;
     const int nperm = rcfg->propagation == B200PETS_PROP_FIXED_MODEL ? 1 : H;
-    rc = b200pets_eval_sequences(model, &rc_it, obs0, pop, perms ? perms + (size_t)it * nperm * B : nullptr,
-                                 eps ? eps + (size_t)it * H * B * model->desc.out_size : nullptr, values, nullptr, eval_ws,
-                                 eval_bytes, stream);
+    float* totals = nullptr;
+    rc = eval_rows(model, &rc_it, obs0, pop, perms ? perms + (size_t)it * nperm * B : nullptr,
+                   eps ? eps + (size_t)it * H * B * model->desc.out_size : nullptr, nullptr, eval_ws, eval_bytes, stream,
+                   &totals);
     if (rc) return rc;
+    // particle mean + NaN rule + top-k + refit in ONE kernel (3 launches per iteration: sample, rollout, refit)
+    rc = launch_cem_update_rows(N, dims, ccfg->elite_num, ccfg->alpha, 1, ccfg->clipped_normal, pop, totals, P, values, mu,
+                                disp, best_val, best_sol, upd_ws, upd_bytes, stream);
+    if (rc) return rc;
+    // NB: values_out then holds the values AFTER the reference's in-place NaN rule (trajectory_opt.py:178)
     if (values_out) CUDA_TRY(cudaMemcpyAsync(values_out + (size_t)it * N, values, sizeof(float) * N, cudaMemcpyDeviceToDevice, stream));
-    rc = b200pets_cem_update(N, dims, ccfg->elite_num, ccfg->alpha, 1, ccfg->clipped_normal, pop, values, mu, disp, best_val,
-                             best_sol, nullptr, nullptr, upd_ws, upd_bytes, stream);
-    if (rc) return rc;
   }
   CUDA_TRY(cudaMemcpyAsync(solution, ccfg->return_mean_elites ? mu : best_sol, sizeof(float) * dims, cudaMemcpyDeviceToDevice, stream));
   return B200PETS_OK;

@@ -401,6 +401,100 @@ __global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArg
 }
 
 
+// Small populations (every PETS configuration: n <= 2048) with the elite rows staged in shared memory: one CTA,
+// six short phases, no global scratch.  Optionally fuses the particle mean (model_env.py:190-191) in front: values
+// are then computed from the per-row totals of the rollout kernel.  Same selection rule as cem_select_kernel (NaN ->
+// -1e-10, top-k by value, ties -> lowest index, elite_idx ascending); mean / variance are summed per coordinate over the
+// elites in ascending index order (a fixed order: the refit is bit-identical however the population was sharded).
+__global__ void __launch_bounds__(kSelThreads, 1)
+cem_select_small_kernel(const SelArgs s, const float* __restrict__ row_totals, int P) {
+  extern __shared__ float esm[];  // [k][dims] elite rows
+  __shared__ float sv[kSmallN];
+  __shared__ unsigned char sf[kSmallN];
+  __shared__ int eidx[kSmallN];
+  __shared__ int sh_best;
+  const int tid = threadIdx.x;
+  const int n = s.n, k = s.k, dims = s.dims;
+  for (int i = tid; i < n; i += kSelThreads) {
+    float v;
+    if (row_totals) {
+      float acc = 0.f;
+      for (int p = 0; p < P; ++p) acc += row_totals[(size_t)i * P + p];
+      v = acc / (float)P;
+    } else {
+      v = s.values[i * s.vstride];
+    }
+    const bool nan = isnan(v);
+    if (nan) v = -1e-10f;  // trajectory_opt.py:178, in place like the reference
+    if (nan || row_totals) s.values[i * s.vstride] = v;
+    sv[i] = v;
+  }
+  if (tid == 0) sh_best = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += kSelThreads) {
+    const float vi = sv[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float vj = sv[j];
+      rank += (vj > vi || (vj == vi && j < i)) ? 1 : 0;
+    }
+    sf[i] = rank < k ? 1 : 0;
+    if (rank == 0) sh_best = i;  // the maximum, lowest index on ties
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kSelThreads) {
+    if (sf[i]) {
+      int pos = 0;
+      for (int j = 0; j < i; ++j) pos += sf[j];
+      eidx[pos] = i;
+      s.elite_idx[pos] = i;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < k * dims; idx += kSelThreads) {
+    const int e = idx / dims, d = idx - e * dims;
+    esm[idx] = s.pop[eidx[e] * s.pstride + d];
+  }
+  const int bi = sh_best;
+  const float bv = sv[bi];
+  const bool better = s.mode == 0 && bv > *s.best_value;  // read before anybody writes it
+  __syncthreads();
+  if (s.mode == 1) {  // records [k][1 + dims]
+    for (int idx = tid; idx < k * (dims + 1); idx += kSelThreads) {
+      const int j = idx / (dims + 1), c = idx - j * (dims + 1);
+      s.records[idx] = c == 0 ? sv[eidx[j]] : esm[j * dims + (c - 1)];
+    }
+    return;
+  }
+  for (int d = tid; d < dims; d += kSelThreads) {
+    float acc = 0.f;
+    for (int e = 0; e < k; ++e) acc += esm[e * dims + d];
+    const float mean = acc / (float)k;
+    float acc2 = 0.f;
+    for (int e = 0; e < k; ++e) {
+      const float df = esm[e * dims + d] - mean;
+      acc2 += df * df;
+    }
+    const float var = acc2 / (float)(s.unbiased ? (k - 1) : k);
+    const float nd = s.use_std ? sqrtf(var) : var;
+    s.mu[d] = s.alpha * s.mu[d] + (1.0f - s.alpha) * mean;
+    s.disp[d] = s.alpha * s.disp[d] + (1.0f - s.alpha) * nd;
+    if (better) s.best_solution[d] = s.pop[bi * s.pstride + d];
+  }
+  if (s.elites_out) {  // rows by descending value (ties: lower population index first), trajectory_opt.py:475-476
+    for (int e = tid; e < k; e += kSelThreads) {
+      const float ve = sv[eidx[e]];
+      int rank = 0;
+      for (int f = 0; f < k; ++f) {
+        const float vf = sv[eidx[f]];
+        rank += (vf > ve || (vf == ve && f < e)) ? 1 : 0;
+      }
+      for (int d = 0; d < dims; ++d) s.elites_out[(size_t)rank * dims + d] = esm[e * dims + d];
+    }
+  }
+  if (better && tid == 0) *s.best_value = bv;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // MPPI (mbrl/planning/trajectory_opt.py:191-311)
 // ------------------------------------------------------------------------------------------------------
@@ -498,6 +592,8 @@ mppi_update_kernel(int n, int dims, float gamma, const float* __restrict__ pop, 
 // ------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------
+int launch_particle_mean(int N, int P, const float* total, float* returns, cudaStream_t stream);
+
 extern "C" {
 
 int b200pets_cem_sample_shard(int32_t population, int32_t first_sequence, int32_t dims, const float* mu,
@@ -529,7 +625,7 @@ size_t b200pets_cem_update_workspace_bytes(int32_t population, int32_t dims, int
 static int run_select(int mode, int n, int dims, int k, float alpha, int unbiased, int use_std, const float* pop,
                       long long pstride, float* values, long long vstride, float* mu, float* disp, float* best_value,
                       float* best_solution, int32_t* elite_idx, float* elites_out, float* records, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      size_t workspace_bytes, void* stream, const float* row_totals = nullptr, int particles = 1) {
   if (n <= 0 || dims <= 0 || k <= 0 || k > n)
     return b200pets_set_error(B200PETS_EINVAL, "cem_update: need 0 < elite_num (%d) <= population (%d)", k, n);
   if (mode == 0 && unbiased && k < 2)
@@ -542,6 +638,18 @@ static int run_select(int mode, int n, int dims, int k, float alpha, int unbiase
   s.best_value = best_value; s.best_solution = best_solution; s.elites_out = elites_out; s.records = records;
   s.partial = reinterpret_cast<float*>(workspace);
   s.elite_idx = elite_idx ? elite_idx : reinterpret_cast<int*>(reinterpret_cast<float*>(workspace) + 33 * (size_t)dims);
+  if (n <= kSmallN && (size_t)k * dims * sizeof(float) <= 150 * 1024) {  // the PETS configurations: elites in smem
+    const size_t esm = (size_t)k * dims * sizeof(float);
+    CUDA_TRY(cudaFuncSetAttribute(cem_select_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+    cem_select_small_kernel<<<1, kSelThreads, esm, (cudaStream_t)stream>>>(s, row_totals, particles);
+    CUDA_TRY(cudaGetLastError());
+    return B200PETS_OK;
+  }
+  if (row_totals) {  // large populations: particle mean as its own (multi-CTA) kernel, then the radix-select path
+    if (vstride != 1) return b200pets_set_error(B200PETS_EINVAL, "cem_update: row totals need contiguous values");
+    int rcm = launch_particle_mean(n, particles, row_totals, values, (cudaStream_t)stream);
+    if (rcm) return rcm;
+  }
   size_t dyn = 0;
   if ((size_t)33 * dims * sizeof(float) <= 160 * 1024) {  // partial sums in shared memory (latency-bound reduction)
     dyn = (size_t)33 * dims * sizeof(float);
@@ -640,6 +748,17 @@ int b200pets_shift_solution(int32_t horizon, int32_t act_dim, int32_t replan_fre
 }
 
 }  // extern "C"
+
+// internal (api.cu, fused plan): refit straight from the rollout kernel's per-row totals [N][P] (particle mean fused)
+int launch_cem_update_rows(int population, int dims, int elite_num, float alpha, int unbiased, int use_std,
+                           const float* population_in, const float* row_totals, int particles, float* values, float* mu,
+                           float* dispersion, float* best_value, float* best_solution, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return run_select(0, population, dims, elite_num, alpha, unbiased, use_std, population_in, dims, values, 1, mu,
+                    dispersion, best_value, best_solution, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream,
+                    row_totals, particles);
+}
+
 
 int launch_particle_mean(int N, int P, const float* total, float* returns, cudaStream_t stream) {
   particle_mean_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, P, total, returns);

@@ -18,6 +18,8 @@
 // packed weight image carries bf16(b) and bf16(b - bf16(b)) in the matching K rows (api.cu pack kernel).
 //
 // Reference semantics restated: see rollout_f32.cu header (same per-row maths, same file:line anchors).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -28,12 +30,10 @@ struct TcPlan {
   int nblk[B200PETS_MAX_LAYERS];  // K-blocks (64 K-elements) per layer
   uint32_t stage_bytes;
   int nstages;
-  uint32_t off_A, off_ring, off_obs, off_act, off_const, off_bar;
+  uint32_t off_A, off_ring, off_obs, off_act, off_const, off_cout, off_bar;
   uint32_t tmem_cols;
   int obs_ld, act_ld;
   int h0n;  // columns of the first N half of the hidden layers
-  int kr;   // K-round pipeline with two accumulators (all padded widths <= 208, layer-0 K <= 192)
-  uint32_t off_atail;  // KR: 128 x 16 bf16 tile (K columns 192..207 of the A operand), canonical no-swizzle K-major
   uint32_t smem_bytes;
 };
 
@@ -43,9 +43,6 @@ constexpr int kEpiSplit = 4;  // column splits of the epilogue (16 epilogue warp
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kCemTabDims = 1024;  // horizon * act_dim supported by the fused CEM iteration
-// KR TMEM map: accumulator 0 = [0, 208), accumulator 1 = [208, 416), activations (A operand, K columns 0..191) = [416, 512)
-constexpr uint32_t kAcc1 = 208, kActKR = 416;
-constexpr int kTmemKSteps = 12;  // K steps whose A operand fits the 96 activation columns; later ones come from smem
 
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
@@ -53,6 +50,16 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float sqrt_approx(float x) {  // one MUFU op, no slow-path fix-up (argument is in [1, inf))
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -83,7 +90,7 @@ struct InDims {
 };
 static __device__ __noinline__ void build_input_tmem(const InDims m, const float* my_obs, const float* arow,
                                                      const float* c_mean, const float* c_istd, uint32_t a_out, int cs,
-                                                     int CS, uint64_t* bars, int nbars) {
+                                                     int CS, uint64_t* bar_ar) {
   const int Kp0 = m.Kp0;
   // Work unit = 8 operand columns (4 TMEM columns, one tcgen05.st.x4), dealt round-robin to the CS column-split warps
   // of the row: with Kp0 = 32 every warp has exactly one unit (the 16-column split left half of the warps idle).
@@ -112,7 +119,8 @@ static __device__ __noinline__ void build_input_tmem(const InDims m, const float
   }
   tmem_st_wait();
   tc_fence_before();
-  for (int b = 0; b < nbars; ++b) mbar_arrive(&bars[b]);  // both halves (v3) / every round of layer 0 (KR)
+  mbar_arrive(&bar_ar[0]);
+  mbar_arrive(&bar_ar[1]);
 }
 
 // Actions of (sequence n, step t) drawn from the CEM sampling distribution with exactly the Philox keying of
@@ -258,10 +266,7 @@ static __device__ __noinline__ void cem_tail_refit(const TailArgs* ap, int dims,
 //
 // TMEM columns: [0, 256) accumulators (hidden: halves at 0 and h0n; output layer at 0), [256, 384) and [384, 512)
 // the two activation buffers (layer g reads buffer g & 1 and its epilogue writes buffer (g + 1) & 1).
-// KR (K-round pipeline): two accumulators (layer g -> accumulator g & 1), one activation buffer; the epilogue hands the
-// next layer's A operand over in rounds of four 16-column chunks and the MMA warp issues a round's K steps (full N)
-// while the next round's activation pass runs.
-template <int ACT, int CS, bool CEMF, bool KR>  // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
+template <int ACT, int CS, bool CEMF>  // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
 __global__ void __launch_bounds__(64 + 128 * CS, 1)
 rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ RolloutArgs a, const __grid_constant__ TcPlan p,
                   const long long num_tiles) {
@@ -273,17 +278,16 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
   float* act_s = reinterpret_cast<float*>(smem + p.off_act);
   float* c_mean = reinterpret_cast<float*>(smem + p.off_const);
   float* c_istd = c_mean + m.in;
-  float* c_minlv = c_istd + m.in;
-  float* c_maxlv = c_minlv + m.out;
-  float* c_nodelta = c_maxlv + m.out;  // [D] 1.0 = keep raw prediction
-  float* rew_s = c_nodelta + m.D;      // [128] learned-reward column of the current step
+  // per-output constants of the output-layer epilogue, one 16-byte load per output (padded to a multiple of 4 outputs):
+  //   x = max_logvar * log2(e), y = exp(max_logvar - min_logvar), z = exp(min_logvar / 2), w = 1 if the prediction is a
+  //   delta to add to the old observation (0: keep the raw prediction -- no_delta columns, the learned-reward column, pad)
+  const int outq = (m.out + 3) & ~3;
+  float4* c_out = reinterpret_cast<float4*>(smem + p.off_cout);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* bar_empty = bar_full + kMaxStages;
   uint64_t* bar_ar = bar_empty + kMaxStages;  // [2] activations of half h written (count: all epilogue threads)
-  uint64_t* bar_acc = bar_ar + 2;             // [2] accumulator of half h complete (tcgen05.commit); KR uses [0] only
-  uint64_t* bar_k = bar_acc + 2;              // [4] KR: activations of round r written (count: all epilogue threads)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_k + 4);
-  static_assert(!KR || CS == 4, "the K-round pipeline deals chunk 4r + cs to column split cs");
+  uint64_t* bar_acc = bar_ar + 2;             // [2] accumulator of half h complete (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.nstages;
@@ -303,7 +307,6 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
     mbar_init(&bar_ar[1], kEpiThreads);
     mbar_init(&bar_acc[0], 1);
     mbar_init(&bar_acc[1], 1);
-    for (int r = 0; r < 4; ++r) mbar_init(&bar_k[r], kEpiThreads);
     mbar_fence_init();
   }
   for (int j = threadIdx.x; j < m.in; j += kThreadsAll) {
@@ -312,17 +315,14 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
   }
   // logvar clamp folded into two per-output constants (see the output-layer epilogue):
   //   var = exp(min + softplus(max - softplus(max - lv) - min)) = exp(min) * (1 + exp(max - min) / (1 + exp(max - lv)))
-  float* c_sdmin = c_minlv;  // exp(0.5 * min_logvar)
-  float* c_ratio = c_nodelta + m.D + kTileM;  // exp(max_logvar - min_logvar)
-  float* cem_tab = c_ratio + m.out;           // [2][kCemTabDims]: sampling mean, sqrt(constrained variance) (fused CEM)
+  float* cem_tab = reinterpret_cast<float*>(c_out + outq);  // [2][kCemTabDims]: sampling mean, sqrt(constrained variance) (fused CEM)
   __shared__ int sh_tail[2];
-  for (int j = threadIdx.x; j < m.out; j += kThreadsAll) {
-    const float mn = m.deterministic ? 0.f : m.min_lv[j], mx = m.deterministic ? 0.f : m.max_lv[j];
-    c_sdmin[j] = expf(0.5f * mn);
-    c_maxlv[j] = mx;
-    c_ratio[j] = expf(mx - mn);
+  for (int j = threadIdx.x; j < outq; j += kThreadsAll) {
+    const bool real = j < m.out;
+    const float mn = (m.deterministic || !real) ? 0.f : m.min_lv[j], mx = (m.deterministic || !real) ? 0.f : m.max_lv[j];
+    const bool delta = real && j < m.D && m.target_is_delta && !m.no_delta[j];
+    c_out[j] = make_float4(mx * 1.4426950408889634f, expf(mx - mn), expf(0.5f * mn), delta ? 1.f : 0.f);
   }
-  for (int j = threadIdx.x; j < m.D; j += kThreadsAll) c_nodelta[j] = (!m.target_is_delta || m.no_delta[j]) ? 1.f : 0.f;
   const int cem_dims = a.H * m.A;
   if (CEMF && a.cem_mu) {
     for (int d = threadIdx.x; d < cem_dims; d += kThreadsAll) {
@@ -384,59 +384,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
     // =========================== MMA issuer ===========================
     // The whole warp runs the control flow converged (waits are uniform); the MMAs and commits are issued by the one
     // elected lane, always the same one, so that every tcgen05.commit tracks all MMAs issued before it.
-    if (KR) {
-      int stage = 0;
-      uint32_t phase = 0, kpar = 0;  // kpar: one parity bit per round barrier
-      uint32_t g = 0;                // global layer counter: selects the accumulator
-      const uint32_t ring_addr = smem_u32(ring);
-      const uint64_t adesc_tail = umma_smem_desc(smem_u32(smem + p.off_atail), 2048u, 128u);
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int t = a.t0; t < a.t1; ++t) {
-          for (int l = 0; l < nlayers; ++l, ++g) {
-            const bool stamp = a.timeline && lane == 0 && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x;
-            const int nk = m.Kp[l] >> 4;
-            const int rounds = (nk + 3) >> 2;
-            const uint32_t np = (uint32_t)m.Np[l];
-            const uint32_t b_lbo = np * 16u;
-            const uint32_t acc = tmem_base + ((g & 1u) ? kAcc1 : 0u);
-            const uint32_t a_col = tmem_base + kActKR;
-            const uint32_t slot_addr = ring_addr + (uint32_t)stage * p.stage_bytes;
-            const uint32_t slot_phase = phase;
-            uint64_t* slot_empty = &bar_empty[stage];
-            uint64_t* slot_full = &bar_full[stage];
-            if (++stage == S) { stage = 0; phase ^= 1u; }
-            const uint32_t idesc = umma_idesc_bf16_m128(np);
-            const uint64_t b_inc = (uint64_t)((2u * b_lbo) >> 4);  // descriptor start-address step per K step
-            if (stamp) a.timeline[64 + l * 4 + 0] = clock64();
-            mbar_wait(slot_full, slot_phase);
-            const uint64_t bdesc = umma_smem_desc(slot_addr, b_lbo, 128u);
-            for (int r = 0; r < rounds; ++r) {
-              mbar_wait(&bar_k[r], (kpar >> r) & 1u);
-              kpar ^= 1u << r;
-              tc_fence_after();
-              if (stamp && r == 0) a.timeline[64 + l * 4 + 1] = clock64();
-              if (elect_one()) {
-                const int k1 = min(4 * r + 4, nk);
-                uint64_t bd = bdesc + (uint64_t)(4 * r) * b_inc;
-                uint32_t acol = a_col + 8u * (uint32_t)(4 * r);
-                for (int kk = 4 * r; kk < k1; ++kk) {
-                  if (kk < kTmemKSteps) umma_bf16_ts(acc, acol, bd, idesc, kk != 0 ? 1u : 0u);
-                  else umma_bf16_ss(acc, adesc_tail, bd, idesc, 1u);  // K columns 192..207 from the shared-memory tile
-                  bd += b_inc;
-                  acol += 8u;
-                }
-                if (r == rounds - 1) {
-                  umma_commit(&bar_acc[0]);
-                  umma_commit(slot_empty);
-                }
-              }
-              __syncwarp();
-            }
-            if (stamp) a.timeline[64 + l * 4 + 3] = clock64();
-          }
-        }
-      }
-    } else {
+    {
       int stage = 0;
       uint32_t phase = 0, ar_par = 0;
       uint32_t g = 0;  // global layer counter: selects the activation buffer
@@ -535,9 +483,8 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
 
     const InDims in_dims{m.Kp[0], m.D, m.Dp, m.A, m.in, m.obs_process};
     auto build_input = [&](int tt) {
-      if (KR) build_input_tmem(in_dims, my_obs, act_buf(tt), c_mean, c_istd, t_lane + kActKR, cs, CS, bar_k,
-                               ((in_dims.Kp0 >> 4) + 3) >> 2);
-      else build_input_tmem(in_dims, my_obs, act_buf(tt), c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs, CS, bar_ar, 2);
+      build_input_tmem(in_dims, my_obs, act_buf(tt), c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs,
+                       CS, bar_ar);
     };
 
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -560,7 +507,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
       auto score = [&](int ts) {
         const float* arow = act_buf(ts);
         // model_env.py:124-128: pred_rewards only when reward_fn is None, an explicit reward_fn always wins
-        float rew = m.reward_fn == B200PETS_REWARD_LEARNED ? rew_s[i] : reward_eval(m.reward_fn, arow, m.A, 1, my_obs, m.D, 1);
+        float rew = m.reward_fn == B200PETS_REWARD_LEARNED ? my_obs[m.D] : reward_eval(m.reward_fn, arow, m.A, 1, my_obs, m.D, 1);
         const bool done = term_eval(m.term_fn, my_obs, m.D, 1);
         if (valid) {
           if (a.reward_out) a.reward_out[rid] = rew;
@@ -618,53 +565,6 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
           const int n_true = m.N[l];
           const int kp_next = m.Kp[l + 1];
           const uint32_t a_out = t_lane + 256u + (((g + 1u) & 1u) << 7);
-          if (KR) {
-            const uint32_t acc_rd = t_lane + ((g & 1u) ? kAcc1 : 0u);
-            mbar_wait(&bar_acc[0], acc0_par);
-            acc0_par ^= 1u;
-            tc_fence_after();
-            if (stamp) a.timeline[sp++] = clock64();  // accumulator ready
-            const int nk_next = kp_next >> 4;
-            const int rounds = (nk_next + 3) >> 2;
-            for (int r = 0; r < rounds; ++r) {
-              const int c = 4 * r + cs;
-              if (c < nk_next) {
-                float v[16];
-                if (16 * c < NpH) {
-                  uint32_t rr[16];
-                  tmem_ld16(acc_rd + (uint32_t)(16 * c), rr);
-                  tmem_ld_wait();
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) v[e] = act_tc<ACT>(__uint_as_float(rr[e]), m.leaky);
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) v[e] = 0.f;
-                }
-                if (16 * c + 15 >= n_true && 16 * c <= n_true + 1) {
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) {
-                    const int col = 16 * c + e;
-                    if (col == n_true || col == n_true + 1) v[e] = 1.f;
-                  }
-                }
-                uint32_t pk[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
-                if (c < kTmemKSteps) {
-                  tmem_st8(t_lane + kActKR + (uint32_t)(8 * c), pk);
-                } else {  // K columns 192..207: shared-memory tile of the SS-form K step (two 16-byte core-matrix rows)
-                  uint8_t* at = smem + p.off_atail;
-                  *reinterpret_cast<uint4*>(at + a_chunk_off(i, 0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                  *reinterpret_cast<uint4*>(at + a_chunk_off(i, 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                  fence_proxy_async_smem();
-                }
-              }
-              tmem_st_wait();
-              tc_fence_before();
-              mbar_arrive(&bar_k[r]);
-              if (stamp && (r == 0 || r + 2 >= rounds)) a.timeline[sp++] = clock64();  // first / last two rounds handed over
-            }
-          } else
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h == 0) {
@@ -748,7 +648,6 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         }
 
         // ---- output layer: groups of 4 outputs; Gaussian sample, delta add-back (branch-free inner maths) ----
-        const uint32_t t_out = t_lane + ((KR && (g & 1u)) ? kAcc1 : 0u);  // KR: the output layer's accumulator is g & 1
         mbar_wait(&bar_acc[0], acc0_par);
         acc0_par ^= 1u;
         ++g;
@@ -756,14 +655,18 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         if (stamp) a.timeline[sp++] = clock64();  // output accumulator ready
         for (int gq = CS - 1 - cs; gq < ngroups; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
           uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
-          tmem_ld4(t_out + (uint32_t)(4 * gq), rm);
-          if (!m.deterministic) tmem_ld4(t_out + (uint32_t)(m.outp + 4 * gq), rl);
+          tmem_ld4(t_lane + (uint32_t)(4 * gq), rm);
+          if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rl);
           tmem_ld_wait();
           const int u = (gq - (CS - 1 - cs)) / CS;
           if (stamp) a.timeline[40 + 4 * u] = clock64();
-          float pred[4];
+          // Branch-free per output: one 16-byte constant load, 3 MUFU (ex2, rcp, sqrt), one LDS + FADD/FSEL + STS of the state.
+          //   var = exp(min + softplus(max - softplus(max - lv) - min)) = e^min * (1 + e^(max-min) / (1 + e^(max-lv)))
+          //   (gaussian_mlp.py:150-153 folded into two per-output constants), pred = mean + sqrt(var) * z
+          //   (model.py:467-471), next = pred + keep * old (one_dim_tr_model.py:281-286).  Padded outputs (o >= out)
+          //   land in the row's padding words; the learned-reward column is word D of the row.
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
           if (draw) {
-            float z[4];
             if (a.eps) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -776,29 +679,21 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             } else {
               philox_normal4((uint32_t)rid_glob, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z);
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int oc = min(4 * gq + e, m.out - 1);
-              const float e1 = __expf(c_maxlv[oc] - __uint_as_float(rl[e]));        // exp(max - lv)   (inf is fine)
-              const float e2 = __fdividef(c_ratio[oc], 1.f + e1);                  // exp(max - min) / (1 + e1)
-              const float sd = c_sdmin[oc] * sqrt_approx(1.f + e2);                // sqrt(exp(clamped logvar))
-              pred[e] = fmaf(sd, z[e], __uint_as_float(rm[e]));
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pred[e] = __uint_as_float(rm[e]);
           }
-          if (stamp) a.timeline[41 + 4 * u] = (long long)__float_as_uint(pred[0] + pred[1] + pred[2] + pred[3]) * 0 + clock64();
+          if (stamp) a.timeline[41 + 4 * u] = clock64();
+          const float4* cg = c_out + 4 * gq;
+          float* og = my_obs + 4 * gq;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int o = 4 * gq + e;
-            if (o < m.out) {
-              if (m.learned_rewards && o == m.out - 1) {
-                rew_s[i] = pred[e];
-              } else {
-                my_obs[o] = c_nodelta[o] != 0.f ? pred[e] : pred[e] + my_obs[o];
-              }
+            const float4 c = cg[e];
+            float pred = __uint_as_float(rm[e]);
+            if (draw) {
+              const float e1 = ex2_approx(fmaf(__uint_as_float(rl[e]), -1.4426950408889634f, c.x));  // exp(max - lv)   (inf is fine)
+              const float e2 = c.y * rcp_approx(1.f + e1);                                          // exp(max - min) / (1 + e1)
+              const float sd = c.z * sqrt_approx(1.f + e2);                                         // sqrt(exp(clamped logvar))
+              pred = fmaf(sd, z[e], pred);
             }
+            og[e] = c.w != 0.f ? pred + og[e] : pred;  // a select, not old * 0: a stale Inf / NaN word must not leak
           }
           if (stamp) a.timeline[42 + 4 * u] = clock64();
         }
@@ -1093,26 +988,31 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   p.stage_bytes = (stage + 127u) & ~127u;
   p.tmem_cols = 512;
   (void)tm;
-  p.h0n = ((m.Np[0] / 16 + 1) / 2) * 16;  // e.g. 208 -> 112 + 96
+  // N split of the hidden layers (16-column chunks): half 0 takes ~9/13 of them.  After half 1's activations arrive only
+  // the K steps that read them (4 of 13 at width 208) are left before half 0's accumulator of the next layer completes,
+  // and half 1's shorter epilogue still covers the next layer's first 9 K steps (measured: 208 -> 144 + 64).
+  {
+    const int C = m.Np[0] / 16;
+    int c0 = (C * 9 + 6) / 13;
+    static const int c0_env = [] { const char* e = getenv("B200PETS_TC_H0CHUNKS"); return e ? atoi(e) : 0; }();  // A/B switch
+    if (c0_env > 0) c0 = c0_env;
+    c0 = max(1, min(C - 1, c0));
+    p.h0n = c0 * 16;
+  }
   if (m.Np[0] - p.h0n < 16) return false;
-  p.obs_ld = m.D | 1;
+  const int outq = (m.out + 3) & ~3;
+  p.obs_ld = max(m.D, outq) | 1;  // a row holds the D observation words, the learned-reward word and the output padding
   p.act_ld = m.A | 1;
   uint32_t off = 0;
   p.off_A = 0;
   p.off_obs = off; off += (uint32_t)kTileM * p.obs_ld * 4;
   p.off_act = off; off += 3u * (uint32_t)kTileM * p.act_ld * 4;
-  p.off_const = off; off += (uint32_t)(2 * m.in + 3 * m.out + m.D + kTileM + 2 * kCemTabDims) * 4;
+  p.off_const = off; off += (uint32_t)(2 * m.in) * 4;
   off = (off + 15u) & ~15u;
-  p.off_bar = off; off += (2 * kMaxStages + 4 + 4) * 8 + 16;
+  p.off_cout = off; off += (uint32_t)(4 * outq + 2 * kCemTabDims) * 4;
+  off = (off + 15u) & ~15u;
+  p.off_bar = off; off += (2 * kMaxStages + 4) * 8 + 16;
   off = (off + 127u) & ~127u;
-  // K-round pipeline: every padded width must fit one of two 208-column accumulators, the A operand 96 TMEM columns
-  // (+ one shared-memory K step), and the layer-0 operand must not need the shared-memory tile
-  p.kr = 1;
-  for (int l = 0; l < p.nlayers; ++l)
-    if (m.Np[l] > (int)kAcc1 || m.Kp[l] > 16 * (kTmemKSteps + 1)) p.kr = 0;
-  if (m.Kp[0] > 16 * kTmemKSteps) p.kr = 0;
-  p.off_atail = off;
-  if (p.kr) off += (uint32_t)kTileM * 16u * 2u;
   p.off_ring = off;
   int S = ((int)max_smem - (int)off) / (int)p.stage_bytes;
   if (S < 1) return false;  // S >= 2: one layer in use, the next one in flight; S == 1 (wide layers): no prefetch
@@ -1147,17 +1047,18 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
   const unsigned grid = (unsigned)min((long long)g_sm_count, tiles);
   const bool cemf = a.cem_mu != nullptr || a.tail_counter != nullptr;
   void (*kern)(const ModelDev, const RolloutArgs, const TcPlan, const long long) = nullptr;
-  static const bool kr_off = [] { const char* e = getenv("B200PETS_TC_KR"); return e && e[0] == '0'; }();  // A/B switch
-  const bool kr = p.kr && !kr_off;
-#define B200PETS_PICK(ACTV)                                                                                              \
-  kern = cemf ? (kr ? rollout_tc_kernel<ACTV, kEpiSplit, true, true> : rollout_tc_kernel<ACTV, kEpiSplit, true, false>)   \
-              : (kr ? rollout_tc_kernel<ACTV, kEpiSplit, false, true> : rollout_tc_kernel<ACTV, kEpiSplit, false, false>)
   switch (m.act) {
-    case B200PETS_ACT_SILU: B200PETS_PICK(B200PETS_ACT_SILU); break;
-    case B200PETS_ACT_RELU: B200PETS_PICK(B200PETS_ACT_RELU); break;
-    default: B200PETS_PICK(B200PETS_ACT_LEAKY_RELU); break;
+    case B200PETS_ACT_SILU:
+      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, true> : rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, false>;
+      break;
+    case B200PETS_ACT_RELU:
+      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, true> : rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, false>;
+      break;
+    default:
+      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, true>
+                  : rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, false>;
+      break;
   }
-#undef B200PETS_PICK
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
   kern<<<grid, 64 + 128 * kEpiSplit, p.smem_bytes, stream>>>(m, a, p, tiles);
   CUDA_TRY(cudaGetLastError());
