@@ -172,6 +172,30 @@ int b200pets_step(b200pets_model_t model, int32_t precision, int32_t propagation
                   uint64_t offset, int32_t sample, float* next_obs, float* reward, uint8_t* done,
                   void* stream);
 
+/* ---- MBPO model rollouts kept on the device (mbrl/algorithms/mbpo.py:31-63) ------------------------------ */
+
+/* The `accum_dones` bookkeeping of rollout_model_and_populate_sac_buffer (mbpo.py:44,51-62) for one step:
+ *   alive[r] = !accum_dones[r]   (the rows of this step that go to sac_buffer.add_batch)
+ *   accum_dones[r] |= done[r]
+ * all [dev] uint8[batch]. */
+int b200pets_mbpo_mask(int64_t batch, const uint8_t* done, uint8_t* accum_dones, uint8_t* alive, void* stream);
+
+/* Ordered compaction of the alive transitions of `steps` model steps: replaces the per-step device->host copies and
+ * numpy selections `obs[~accum_dones]`, ... of mbpo.py:53-60.  The outputs hold, packed and in (step, row) order -- the
+ * order of the reference's add_batch calls --, the alive rows of every step:
+ *   obs0     [dev] float[B][D]       observations before step 0 (the sampled start states)
+ *   act      [dev] float[steps][B][A]
+ *   next_obs [dev] float[steps][B][D] (the observation before step i > 0 is next_obs[i-1])
+ *   reward   [dev] float[steps][B], done / alive [dev] uint8[steps][B]
+ *   *_out    [dev] sized for steps * B rows
+ *   counts   [dev] int64[steps + 1]: alive rows per step, counts[steps] = total */
+size_t b200pets_mbpo_compact_workspace_bytes(int32_t steps, int64_t batch);
+int b200pets_mbpo_compact(int32_t steps, int64_t batch, int32_t obs_dim, int32_t act_dim, const float* obs0,
+                          const float* act, const float* next_obs, const float* reward, const uint8_t* done,
+                          const uint8_t* alive, float* obs_out, float* act_out, float* next_obs_out,
+                          float* reward_out, uint8_t* done_out, int64_t* counts, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- CEM / iCEM building blocks (mbrl/planning/trajectory_opt.py) ------------------------------------ */
 
 /* CEMOptimizer._sample_population (trajectory_opt.py:110-128) + util.math.truncated_normal_ (util/math.py

@@ -20,6 +20,6 @@ def __getattr__(name):
 
     if name in _LAZY:
         return getattr(importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
-    if name in ("synthetic", "functions", "planning", "models", "model_env", "staging", "_lib", "build", "dist"):
+    if name in ("synthetic", "functions", "planning", "models", "model_env", "staging", "_lib", "build", "dist", "mbpo"):
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -57,6 +57,9 @@ _SIGNATURES = {
     "b200pets_eval_sequences": (C.c_int, [_P, C.POINTER(RolloutCfg), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "b200pets_step": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32,
                                 _P, _P, _P, _P]),
+    "b200pets_mbpo_mask": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
+    "b200pets_mbpo_compact_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
+    "b200pets_mbpo_compact": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [_P] * 12 + [_P, C.c_size_t, _P]),
     "b200pets_cem_sample": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32, _P, _P]),
     "b200pets_cem_sample_shard": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32,
                                             _P, _P]),

@@ -93,28 +93,35 @@ static __device__ __noinline__ void build_input_tmem(const InDims m, const float
                                                      int CS, uint64_t* bar_ar) {
   const int Kp0 = m.Kp0;
   // Work unit = 8 operand columns (4 TMEM columns, one tcgen05.st.x4), dealt round-robin to the CS column-split warps
-  // of the row: with Kp0 = 32 every warp has exactly one unit (the 16-column split left half of the warps idle).
-  // j is warp-uniform, so the case analysis below is uniform branching, not divergence; per element: <= 3 LDS,
-  // FADD, FMUL, FADD instead of the ~21 instructions of the clamped-index form.
+  // of the row: with Kp0 = 32 every warp has exactly one unit.  c_mean / c_istd are Kp0 long ((0, 1) past the real
+  // inputs) and c_mean[Kp0 .. Kp0+2] = {1, 1, 0} is the source of the two bias-one columns and the zero pad, so every
+  // element is "load, subtract, scale" from a warp-uniform source pointer: the eight elements' loads are independent
+  // (the branchy form serialised ~8 x (3 dependent LDS + branches) ~ 1.3 k cycles on the step's critical path).
+  const float* c_one = c_mean + Kp0;
   for (int gi = cs; gi < Kp0 / 8; gi += CS) {
-    float x[8];
+    float raw[8], mu[8], is[8];
+    if (m.obs_process == B200PETS_PROC_NONE) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = gi * 8 + e;
-      float raw = 0.f, mu = 0.f, is = 0.f, cst = 0.f;
-      if (j < m.in) {
-        if (j < m.Dp) raw = m.obs_process == B200PETS_PROC_NONE ? my_obs[j] : proc_obs_elem(my_obs, j, m.obs_process);
-        else raw = arow[j - m.Dp];
-        mu = c_mean[j];
-        is = c_istd[j];
-      } else if (j < m.in + 2) {
-        cst = 1.f;  // the two bias columns
+      for (int e = 0; e < 8; ++e) {
+        const int j = gi * 8 + e;
+        const float* src = j < m.Dp ? my_obs + j : (j < m.in ? arow + (j - m.Dp) : c_one + min(j - m.in, 2));
+        raw[e] = *src;
+        mu[e] = c_mean[j];
+        is[e] = c_istd[j];
       }
-      x[e] = (raw - mu) * is + cst;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {  // generic observation pre-processors (sin / cos columns): cold path
+        const int j = gi * 8 + e;
+        raw[e] = j < m.Dp ? proc_obs_elem(my_obs, j, m.obs_process)
+                          : (j < m.in ? arow[j - m.Dp] : c_one[min(j - m.in, 2)]);
+        mu[e] = c_mean[j];
+        is[e] = c_istd[j];
+      }
     }
     uint32_t pk[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(x[2 * e], x[2 * e + 1]);
+    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16((raw[2 * e] - mu[2 * e]) * is[2 * e], (raw[2 * e + 1] - mu[2 * e + 1]) * is[2 * e + 1]);
     tmem_st4(a_out + (uint32_t)(4 * gi), pk);
   }
   tmem_st_wait();
@@ -277,7 +284,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
   float* obs_s = reinterpret_cast<float*>(smem + p.off_obs);
   float* act_s = reinterpret_cast<float*>(smem + p.off_act);
   float* c_mean = reinterpret_cast<float*>(smem + p.off_const);
-  float* c_istd = c_mean + m.in;
+  float* c_istd = c_mean + m.Kp[0] + 4;  // c_mean[Kp0 .. Kp0+2] = {1, 1, 0}: source of the bias-one / pad columns
   // per-output constants of the output-layer epilogue, one 16-byte load per output (padded to a multiple of 4 outputs):
   //   x = max_logvar * log2(e), y = exp(max_logvar - min_logvar), z = exp(min_logvar / 2), w = 1 if the prediction is a
   //   delta to add to the old observation (0: keep the raw prediction -- no_delta columns, the learned-reward column, pad)
@@ -312,6 +319,10 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
   for (int j = threadIdx.x; j < m.in; j += kThreadsAll) {
     c_mean[j] = m.norm_mode ? m.norm_mean_f[j] : 0.f;
     c_istd[j] = m.norm_mode ? m.norm_istd_f[j] : 1.f;
+  }
+  for (int j = m.in + threadIdx.x; j < m.Kp[0] + 4; j += kThreadsAll) {
+    c_mean[j] = (j == m.Kp[0] || j == m.Kp[0] + 1) ? 1.f : 0.f;
+    if (j < m.Kp[0]) c_istd[j] = 1.f;
   }
   // logvar clamp folded into two per-output constants (see the output-layer epilogue):
   //   var = exp(min + softplus(max - softplus(max - lv) - min)) = exp(min) * (1 + exp(max - min) / (1 + exp(max - lv)))
@@ -653,6 +664,9 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         ++g;
         tc_fence_after();
         if (stamp) a.timeline[sp++] = clock64();  // output accumulator ready
+        // the column split with the most output groups (cs = CS - 1: groups 0, CS, ..) bounds the end-of-step barrier
+        const bool stamp3 = a.timeline && blockIdx.x == 0 && warp == 2 + 4 * (CS - 1) && lane == 0 && t == a.t0 + 5 && tile == blockIdx.x;
+        if (stamp3) a.timeline[56] = clock64();
         for (int gq = CS - 1 - cs; gq < ngroups; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
           uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
           tmem_ld4(t_lane + (uint32_t)(4 * gq), rm);
@@ -684,25 +698,33 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
           const float4* cg = c_out + 4 * gq;
           float* og = my_obs + 4 * gq;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 c = cg[e];
-            float pred = __uint_as_float(rm[e]);
+          for (int h = 0; h < 2; ++h) {  // two outputs at a time: loads up front so that the two chains overlap
+            const float4 c0 = cg[2 * h], c1 = cg[2 * h + 1];
+            const float o0 = og[2 * h], o1 = og[2 * h + 1];
+            float p0 = __uint_as_float(rm[2 * h]), p1 = __uint_as_float(rm[2 * h + 1]);
             if (draw) {
-              const float e1 = ex2_approx(fmaf(__uint_as_float(rl[e]), -1.4426950408889634f, c.x));  // exp(max - lv)   (inf is fine)
-              const float e2 = c.y * rcp_approx(1.f + e1);                                          // exp(max - min) / (1 + e1)
-              const float sd = c.z * sqrt_approx(1.f + e2);                                         // sqrt(exp(clamped logvar))
-              pred = fmaf(sd, z[e], pred);
+              // exp(max - lv) (inf is fine); exp(max - min) / (1 + e1); sqrt(exp(clamped logvar))
+              const float e10 = ex2_approx(fmaf(__uint_as_float(rl[2 * h]), -1.4426950408889634f, c0.x));
+              const float e11 = ex2_approx(fmaf(__uint_as_float(rl[2 * h + 1]), -1.4426950408889634f, c1.x));
+              const float e20 = c0.y * rcp_approx(1.f + e10), e21 = c1.y * rcp_approx(1.f + e11);
+              const float sd0 = c0.z * sqrt_approx(1.f + e20), sd1 = c1.z * sqrt_approx(1.f + e21);
+              p0 = fmaf(sd0, z[2 * h], p0);
+              p1 = fmaf(sd1, z[2 * h + 1], p1);
             }
-            og[e] = c.w != 0.f ? pred + og[e] : pred;  // a select, not old * 0: a stale Inf / NaN word must not leak
+            // a select, not old * 0: a stale Inf / NaN word must not leak
+            og[2 * h] = c0.w != 0.f ? p0 + o0 : p0;
+            og[2 * h + 1] = c1.w != 0.f ? p1 + o1 : p1;
           }
           if (stamp) a.timeline[42 + 4 * u] = clock64();
         }
         tc_fence_before();
         if (stamp) a.timeline[sp++] = clock64();  // outputs sampled
+        if (stamp3) a.timeline[57] = clock64();
         epi_bar();
         if (stamp) a.timeline[sp++] = clock64();  // barrier
         if (more) build_input(t + 1);             // next step's layer 0 starts while the owner scores this step
         if (stamp) a.timeline[sp++] = clock64();  // next input handed over
+        if (stamp3) a.timeline[58] = clock64();
         // ---- reward, termination, accumulate: deferred into a gap of the next step when the model is deep enough ----
         if (scorer && !(more && defer_score)) score(t);
         if (stamp) a.timeline[sp++] = clock64();  // reward done
@@ -1007,7 +1029,7 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   p.off_A = 0;
   p.off_obs = off; off += (uint32_t)kTileM * p.obs_ld * 4;
   p.off_act = off; off += 3u * (uint32_t)kTileM * p.act_ld * 4;
-  p.off_const = off; off += (uint32_t)(2 * m.in) * 4;
+  p.off_const = off; off += (uint32_t)(2 * m.Kp[0] + 4) * 4;
   off = (off + 15u) & ~15u;
   p.off_cout = off; off += (uint32_t)(4 * outq + 2 * kCemTabDims) * 4;
   off = (off + 15u) & ~15u;

@@ -134,7 +134,8 @@ class ModelEnv:
         return state
 
     def step(self, actions, model_state: Dict[str, torch.Tensor], sample: bool = False, *,
-             _perm: Optional[torch.Tensor] = None, _eps: Optional[torch.Tensor] = None, _offset: Optional[int] = None):
+             _perm: Optional[torch.Tensor] = None, _eps: Optional[torch.Tensor] = None, _offset: Optional[int] = None,
+             _out=None):
         assert len(actions.shape) == 2  # batch, action_dim  (model_env.py:108)
         self.staged.ensure_fresh()
         with torch.no_grad():
@@ -158,9 +159,12 @@ class ModelEnv:
             if perm is not None:
                 perm = perm.to(torch.int64).contiguous()
             d = self.staged.desc
-            next_obs = torch.empty_like(obs)
-            reward = torch.empty(B, dtype=torch.float32, device=self.device)
-            done = torch.empty(B, dtype=torch.uint8, device=self.device)
+            if _out is not None:  # caller-owned output buffers (device-resident rollout loops: mbpo.py)
+                next_obs, reward, done = _out
+            else:
+                next_obs = torch.empty_like(obs)
+                reward = torch.empty(B, dtype=torch.float32, device=self.device)
+                done = torch.empty(B, dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.b200pets_step(
                     self.staged.handle, _lib.PREC[self.precision], _lib.PROP[prop], B, _lib.ptr(obs), _lib.ptr(actions),
@@ -171,8 +175,12 @@ class ModelEnv:
             dones = done.view(-1, 1).bool()
             if d.reward_fn == _lib.REWARD["external"]:
                 rewards = self.reward_fn(actions, next_obs)
+                if _out is not None:
+                    reward.copy_(rewards.view(-1))
             if d.term_fn == _lib.TERM["external"]:
                 dones = self.termination_fn(actions, next_obs)
+                if _out is not None:
+                    done.copy_(dones.view(-1))
             next_state = dict(model_state)
             next_state["obs"] = next_obs
             if self._return_as_np:

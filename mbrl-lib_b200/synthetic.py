@@ -134,6 +134,10 @@ _register(CaseSpec("walker_ant", obs_dim=17, act_dim=6, hid_size=72, num_layers=
                    population=20, horizon=8, particles=4, obs0_first=1.2))
 
 
+# MBPO rollouts with terminations (hopper rule): the accum_dones mask of mbpo.py:44-62 is exercised
+_register(CaseSpec("mbpo_hopper_small", obs_dim=11, act_dim=3, hid_size=64, num_layers=2, ensemble_size=4, elites=None,
+                   activation="silu", propagation="random_model", normalize="float64", learned_rewards=True,
+                   reward_fn=None, term_fn="hopper", population=1024, horizon=1, particles=1, obs0_first=1.0))
 # learned reward column AND a named reward_fn (the explicit fn wins, model_env.py:124-128), ant termination
 _register(CaseSpec("ant_learned_fn", obs_dim=27, act_dim=8, hid_size=64, num_layers=2, ensemble_size=3,
                    elites=None, activation="silu", propagation="random_model", normalize="float64",

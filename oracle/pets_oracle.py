@@ -290,6 +290,27 @@ class OracleModel:
         return total.reshape(-1, P).mean(dim=1)
 
 
+def mbpo_rollout(model: "OracleModel", initial_obs, policy, rollout_horizon, perms, eps, assigns=None):
+    """rollout_model_and_populate_sac_buffer (mbrl/algorithms/mbpo.py:31-63) with the model noise injected: returns the
+    list of per-step ``add_batch`` argument tuples (obs, action, next_obs, reward, done) -- the rows ``~accum_dones`` --
+    plus the full per-step arrays for diagnostics.  ``policy(obs) -> action`` stands for ``agent.act(..., batched=True)``;
+    perms[i] / eps[i] (or assigns[i]) are the draws of step i (ModelEnv.step with sample=True)."""
+    obs = torch.as_tensor(np.asarray(initial_obs, dtype=np.float32))
+    accum = torch.zeros(obs.shape[0], dtype=torch.bool)
+    batches, full = [], []
+    for i in range(rollout_horizon):
+        action = policy(obs)
+        nobs, rew, done = model.step(obs, action, None if perms is None else perms[i], eps[i], sample=True,
+                                     assign=None if assigns is None else assigns[i])
+        keep = ~accum
+        batches.append((obs[keep].numpy(), action[keep].numpy(), nobs[keep].numpy(), rew[keep, 0].numpy(),
+                        done[keep, 0].numpy()))
+        full.append((nobs.numpy(), rew[:, 0].numpy(), done[:, 0].numpy(), keep.numpy()))
+        obs = nobs
+        accum = accum | done[:, 0]
+    return batches, full
+
+
 # --------------------------------------------------------------------------------------------------
 # optimisers (mbrl/planning/trajectory_opt.py)
 # --------------------------------------------------------------------------------------------------

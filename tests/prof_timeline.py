@@ -20,6 +20,7 @@ b = buf.cpu().tolist()
 t0 = b[0]
 print("epilogue thread stamps (cycles since step start):", [x - t0 for x in b[:24] if x])
 print("fine stamps:", [x - t0 for x in b[40:56] if x])
+print("column split CS-1 (two output groups): output accumulator ready, groups done, next input handed over:", [x - t0 for x in b[56:59] if x])
 for l in range(5):
     s = b[64 + 4 * l: 68 + 4 * l]
     print(f"mma layer {l}: starts waiting {s[0]-t0}, weights + first activation half ready {s[1]-t0}, all MMAs issued {s[3]-t0}")

@@ -268,3 +268,104 @@ def test_sharded_cem_equals_unsharded_plan(precision):
     assert np.array_equal(sols[0], sols[1])  # every rank holds the same plan without a broadcast
     assert np.array_equal(np.concatenate([vals[0], vals[1]], axis=1), ref_vals)  # per-sequence returns, every iteration
     assert np.array_equal(sols[0], ref)
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 2e-4), ("bf16_tc", 2e-2)])
+def test_mbpo_device_rollout_loop_matches_oracle(precision, tol):
+    """rollout_model_and_populate_sac_buffer (mbpo.py:31-63) with obs / predictions / accum_dones resident on the device
+    and one ordered compaction at the end, against the oracle stepping the same loop with the same injected draws:
+    per-step predictions within the kernel's bar, and the packed transitions EXACTLY the `~accum_dones` rows of the
+    device's own per-step arrays, in the order of the reference's add_batch calls."""
+    from mbrl_lib_b200 import mbpo
+    from oracle import pets_oracle as po
+
+    spec, arrays, env = make_env("mbpo_hopper_small", precision, ts1="perms")
+    B, k = 1024, 4
+    inp = syn.make_step_inputs(spec, B)
+    inp["obs"][:, 1:] *= 0.1  # most rows start inside hopper's alive region (|angle| < 0.2, height > 0.7)
+    g = np.random.default_rng(5)
+    Wp = (0.3 * g.standard_normal((spec.obs_dim, spec.act_dim))).astype(np.float32)
+    perms = [g.permutation(B).astype(np.int64) for _ in range(k)]
+    eps = [g.standard_normal((B, spec.out_size)).astype(np.float32) for _ in range(k)]
+    Wd = torch.from_numpy(Wp).to(DEV)
+
+    class _Agent:
+        def act_torch(self, obs, sample):
+            return torch.tanh(obs @ Wd)
+
+    staging = {}
+    noise = [(torch.from_numpy(perms[i]).to(DEV), torch.from_numpy(eps[i]).to(DEV)) for i in range(k)]
+    obs_p, act_p, nxt_p, rew_p, done_p, counts = mbpo.rollout_on_device(env, inp["obs"], _Agent(), True, k, _noise=noise,
+                                                                         _staging=staging)
+    oracle = _oracle(spec, arrays, False)
+    batches, full = po.mbpo_rollout(oracle, inp["obs"], lambda o: torch.tanh(o @ torch.from_numpy(Wp)), k,
+                                    [torch.from_numpy(p) for p in perms], [torch.from_numpy(e) for e in eps])
+    st = {kk: v.cpu().numpy() for kk, v in staging.items()}
+    # (1) the model steps: rows alive on BOTH sides follow the oracle within the kernel's bar
+    both = np.ones(B, bool)
+    for i in range(k):
+        on, orw, od, okeep = full[i]
+        both &= okeep & st["alive"][i].astype(bool)
+        scale = max(1.0, np.abs(on[both]).max())
+        assert np.abs(st["next_obs"][i][both] - on[both]).max() <= tol * scale, i
+        assert np.abs(st["reward"][i][both] - orw[both]).max() <= tol * scale, i
+        assert (st["done"][i][both].astype(bool) != od[both]).mean() <= (0.002 if precision == "f32" else 0.02)
+        both &= ~(st["done"][i].astype(bool) ^ od)  # a row whose termination flipped at a threshold leaves the comparison
+    assert both.sum() > 0 and st["alive"][k - 1].sum() < B  # the mask is exercised: some rows died, some survive
+    # (2) the compaction: exactly the alive rows of the device's per-step arrays, in (step, row) order
+    lo = 0
+    for i in range(k):
+        keep = st["alive"][i].astype(bool)
+        n = int(keep.sum())
+        assert counts[i] == n
+        src_obs = st["obs0"] if i == 0 else st["next_obs"][i - 1]
+        assert np.array_equal(obs_p[lo:lo + n], src_obs[keep])
+        assert np.array_equal(act_p[lo:lo + n], st["act"][i][keep])
+        assert np.array_equal(nxt_p[lo:lo + n], st["next_obs"][i][keep])
+        assert np.array_equal(rew_p[lo:lo + n], st["reward"][i][keep])
+        assert np.array_equal(done_p[lo:lo + n], st["done"][i][keep])
+        if i + 1 < k:  # accum_dones |= dones (mbpo.py:62)
+            assert np.array_equal(st["alive"][i + 1].astype(bool), keep & ~st["done"][i].astype(bool))
+        lo += n
+    assert lo == len(obs_p)
+    if precision == "f32":  # same row sets as the oracle's add_batch calls when no threshold flipped
+        if all(np.array_equal(st["alive"][i].astype(bool), full[i][3]) for i in range(k)):
+            for i, (bo, ba, bn, br, bd) in enumerate(batches):
+                assert len(bo) == counts[i]
+
+
+def test_mbpo_populate_sac_buffer_api():
+    """Drop-in signature of mbrl/algorithms/mbpo.py:31-63 with stand-in replay buffers; numpy agent fallback."""
+    from mbrl_lib_b200 import mbpo
+
+    spec, arrays, env = make_env("mbpo_hopper_small", "auto", ts1="tile_shuffle")
+    B = 2048
+    inp = syn.make_step_inputs(spec, B)
+    inp["obs"][:, 1:] *= 0.1
+
+    class _Batch:
+        def astuple(self):
+            return (inp["obs"], None, None, None, None, None)
+
+    class _Replay:
+        def sample(self, n):
+            assert n == B
+            return _Batch()
+
+    class _Sac:
+        def __init__(self):
+            self.calls = []
+
+        def add_batch(self, obs, action, next_obs, reward, terminated, truncated):
+            assert obs.shape[1] == spec.obs_dim and action.shape[1] == spec.act_dim and next_obs.shape == obs.shape
+            assert reward.shape == (len(obs),) and terminated.dtype == bool and truncated.dtype == bool and not truncated.any()
+            self.calls.append(len(obs))
+
+    class _NumpyAgent:
+        def act(self, obs, sample=False, batched=False):
+            assert batched and isinstance(obs, np.ndarray)
+            return np.tanh(obs[:, :spec.act_dim]).astype(np.float32)
+
+    sac = _Sac()
+    mbpo.rollout_model_and_populate_sac_buffer(env, _Replay(), _NumpyAgent(), sac, True, 3, B)
+    assert len(sac.calls) == 3 and sac.calls[0] == B and sac.calls[0] >= sac.calls[1] >= sac.calls[2] > 0
