@@ -95,6 +95,11 @@ __global__ void pack_image_kernel(const float* __restrict__ Wg, const float* __r
   *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
 }
 
+// Last kernel of a staging call.  The rollout kernel is launched with programmatic stream serialisation and its weight
+// producer reads the packed images BEFORE griddepcontrol.wait; a plain kernel boundary in between guarantees that the
+// pack kernels above have completed and flushed before a dependent launch can even be considered (common.cuh, PDL).
+__global__ void staging_fence_kernel() {}
+
 }  // namespace
 
 static int stage_model(b200pets_model_s* mdl, const float* const* weights, const float* const* biases,
@@ -154,6 +159,7 @@ static int stage_model(b200pets_model_s* mdl, const float* const* weights, const
     for (int r = 1; r < v.img_replicas; ++r)
       CUDA_TRY(cudaMemcpyAsync(mdl->blob + mdl->off_img + (size_t)r * v.img_replica_stride, mdl->blob + mdl->off_img,
                                (size_t)v.img_member_stride * d.num_members, cudaMemcpyDeviceToDevice, stream));
+  staging_fence_kernel<<<1, 1, 0, stream>>>();
   CUDA_TRY(cudaGetLastError());
   return B200PETS_OK;
 }

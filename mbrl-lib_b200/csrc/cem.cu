@@ -15,6 +15,8 @@ __global__ void cem_sample_kernel(int n, int dims, const float* __restrict__ mu,
                                   const float* __restrict__ lb, const float* __restrict__ ub,
                                   const float* __restrict__ z, unsigned long long seed, unsigned long long offset,
                                   int clipped, float* __restrict__ pop, int seq0) {
+  pdl_trigger();
+  pdl_wait();  // mu / disp come from the previous refit; pop may still be read by the previous iteration's kernels
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n * dims) return;
   const int d = (int)(idx % dims);
@@ -415,6 +417,8 @@ cem_select_small_kernel(const SelArgs s, const float* __restrict__ row_totals, i
   __shared__ int sh_best;
   const int tid = threadIdx.x;
   const int n = s.n, k = s.k, dims = s.dims;
+  pdl_trigger();
+  pdl_wait();  // values / row totals / population are the previous kernels' outputs
   for (int i = tid; i < n; i += kSelThreads) {
     float v;
     if (row_totals) {
@@ -603,10 +607,9 @@ int b200pets_cem_sample_shard(int32_t population, int32_t first_sequence, int32_
   if (population <= 0 || dims <= 0) return b200pets_set_error(B200PETS_EINVAL, "cem_sample: empty population");
   if (first_sequence < 0) return b200pets_set_error(B200PETS_EINVAL, "cem_sample: negative first_sequence");
   long long tot = (long long)population * dims;
-  cem_sample_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      population, dims, mu, dispersion, lower, upper, z, rng_key(seed, offset), offset, clipped_normal, population_out,
-      first_sequence);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(cem_sample_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, population,
+                      dims, mu, dispersion, lower, upper, z, (unsigned long long)rng_key(seed, offset),
+                      (unsigned long long)offset, (int)clipped_normal, population_out, (int)first_sequence));
   return B200PETS_OK;
 }
 
@@ -641,8 +644,7 @@ static int run_select(int mode, int n, int dims, int k, float alpha, int unbiase
   if (n <= kSmallN && (size_t)k * dims * sizeof(float) <= 150 * 1024) {  // the PETS configurations: elites in smem
     const size_t esm = (size_t)k * dims * sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(cem_select_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
-    cem_select_small_kernel<<<1, kSelThreads, esm, (cudaStream_t)stream>>>(s, row_totals, particles);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(cem_select_small_kernel, dim3(1), dim3(kSelThreads), esm, (cudaStream_t)stream, s, row_totals, particles));
     return B200PETS_OK;
   }
   if (row_totals) {  // large populations: particle mean as its own (multi-CTA) kernel, then the radix-select path

@@ -310,6 +310,42 @@ static inline unsigned long long rng_key(unsigned long long seed, unsigned long 
   return seed ^ (offset & 0xFFFFFFFF00000000ull);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The kernels of a plan form a chain  sample -> rollout -> refit -> sample ..
+// on one stream.  Launched with the programmatic-stream-serialization attribute, a kernel may become resident as soon
+// as its predecessor has executed pdl_trigger() in all its CTAs; it then runs its prologue (barrier / TMEM set-up,
+// constant tables, the first weight prefetches -- memory no kernel of the chain writes) and blocks in pdl_wait() until
+// the predecessor grid has completed and flushed, BEFORE its first access to anything the chain produces.  Every
+// kernel of the chain waits before it finishes, so completion is transitive along the chain.  Launch gaps and the
+// rollout kernel's ~6 us prologue thereby overlap the tail of the previous kernel.  B200PETS_PDL=0 disables it.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+#ifdef __CUDACC__
+#include <stdlib.h>
+#include <utility>
+static inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("B200PETS_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#endif
+
 // host-side error plumbing (api.cu)
 int b200pets_set_error(int code, const char* fmt, ...);
 #define CUDA_TRY(expr)                                                                            \

@@ -298,6 +298,11 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.nstages;
+  // Programmatic dependent launch (common.cuh): let the next kernel of the chain become resident now; everything up
+  // to the pdl_wait() below (barriers, TMEM, constant tables, the producer's first weight copies) reads only the
+  // staged model, which no kernel of a plan writes.
+  pdl_trigger();
+  if (CEMF) pdl_wait();  // the fused-CEM variants stage the sampling distribution in their prologue
   if (a.timeline && threadIdx.x == 64 && (blockIdx.x == 0 || blockIdx.x == 40)) {
     long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -498,6 +503,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
                        CS, bar_ar);
     };
 
+    pdl_wait();  // actions / observation / row state are the previous kernels' outputs; ours are written after this
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       bool valid;
       long long rid, rid_glob;  // local row id (n * P + p: indexes actions / state / injected noise), global one (RNG key)
@@ -667,12 +673,25 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         // the column split with the most output groups (cs = CS - 1: groups 0, CS, ..) bounds the end-of-step barrier
         const bool stamp3 = a.timeline && blockIdx.x == 0 && warp == 2 + 4 * (CS - 1) && lane == 0 && t == a.t0 + 5 && tile == blockIdx.x;
         if (stamp3) a.timeline[56] = clock64();
-        for (int gq = CS - 1 - cs; gq < ngroups; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
+        // Slot gq = outputs [4 gq, 4 gq + 4) AND (fused mode) the next step's layer-0 operand columns [4 gq, 4 gq + 4).
+        // Without an observation pre-processor input column j < D IS output j, so the thread that samples an output
+        // also normalises it and writes it straight into the next step's A operand in TMEM (tcgen05.st.x2): no
+        // barrier and no separate input-build pass between two steps (they were ~1.3 k cycles of every step); slots past
+        // the outputs carry the action / bias-one / pad columns.  Pre-processed observations keep the generic builder.
+        // (L >= 4: the next step's actions, written in the gap after hidden layer 2, must be ordered before this point
+        //  by one more accumulator barrier -- the same condition that lets the score be deferred.)
+        const bool fuse_in = more && m.obs_process == B200PETS_PROC_NONE && defer_score;
+        const int nslots = fuse_in ? max(ngroups, in_dims.Kp0 >> 2) : ngroups;
+        const uint32_t a_next = t_lane + 256u + ((g & 1u) << 7);  // A buffer of the next step's layer 0 (g already advanced)
+        const float* anext = act_buf(t + 1);
+        for (int gq = CS - 1 - cs; gq < nslots; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
+          const int u = (gq - (CS - 1 - cs)) / CS;
+          float nw[4] = {0.f, 0.f, 0.f, 0.f};
+          if (gq < ngroups) {
           uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
           tmem_ld4(t_lane + (uint32_t)(4 * gq), rm);
           if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rl);
           tmem_ld_wait();
-          const int u = (gq - (CS - 1 - cs)) / CS;
           if (stamp) a.timeline[40 + 4 * u] = clock64();
           // Branch-free per output: one 16-byte constant load, 3 MUFU (ex2, rcp, sqrt), one LDS + FADD/FSEL + STS of the state.
           //   var = exp(min + softplus(max - softplus(max - lv) - min)) = e^min * (1 + e^(max-min) / (1 + e^(max-lv)))
@@ -712,21 +731,46 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
               p1 = fmaf(sd1, z[2 * h + 1], p1);
             }
             // a select, not old * 0: a stale Inf / NaN word must not leak
-            og[2 * h] = c0.w != 0.f ? p0 + o0 : p0;
-            og[2 * h + 1] = c1.w != 0.f ? p1 + o1 : p1;
+            nw[2 * h] = c0.w != 0.f ? p0 + o0 : p0;
+            nw[2 * h + 1] = c1.w != 0.f ? p1 + o1 : p1;
+            og[2 * h] = nw[2 * h];
+            og[2 * h + 1] = nw[2 * h + 1];
           }
           if (stamp) a.timeline[42 + 4 * u] = clock64();
+          }
+          if (fuse_in && 4 * gq < in_dims.Kp0) {  // next step's operand columns 4 gq .. 4 gq + 3
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * gq + e;
+              const float raw = j < m.D ? nw[e] : (j < m.in ? anext[j - m.D] : c_mean[in_dims.Kp0 + min(j - m.in, 2)]);
+              x[e] = (raw - c_mean[j]) * c_istd[j];
+            }
+            uint32_t pk[2] = {pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3])};
+            tmem_st2(a_next + (uint32_t)(2 * gq), pk);
+          }
         }
-        tc_fence_before();
-        if (stamp) a.timeline[sp++] = clock64();  // outputs sampled
+        if (fuse_in) {  // hand the operand to the MMA warp: both halves' barriers, as build_input_tmem does
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bar_ar[0]);
+          mbar_arrive(&bar_ar[1]);
+        } else {
+          tc_fence_before();
+        }
+        if (stamp) a.timeline[sp++] = clock64();  // outputs sampled (fused mode: next input handed over)
         if (stamp3) a.timeline[57] = clock64();
-        epi_bar();
+        const bool score_now = scorer && !(more && defer_score);
+        // the row's words are written by four warps: a barrier before anything reads the whole row (the generic input
+        // builder, an immediate score).  In fused mode with deferred scoring nothing does until the next step's gaps,
+        // which are ordered behind this point by the accumulator barriers.
+        if (!fuse_in || !(more && defer_score)) epi_bar();
         if (stamp) a.timeline[sp++] = clock64();  // barrier
-        if (more) build_input(t + 1);             // next step's layer 0 starts while the owner scores this step
+        if (more && !fuse_in) build_input(t + 1);  // generic path: next step's layer 0 starts while the owner scores this step
         if (stamp) a.timeline[sp++] = clock64();  // next input handed over
         if (stamp3) a.timeline[58] = clock64();
         // ---- reward, termination, accumulate: deferred into a gap of the next step when the model is deep enough ----
-        if (scorer && !(more && defer_score)) score(t);
+        if (score_now) score(t);
         if (stamp) a.timeline[sp++] = clock64();  // reward done
       }
       // ---- store row state ----
@@ -1082,8 +1126,7 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
       break;
   }
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-  kern<<<grid, 64 + 128 * kEpiSplit, p.smem_bytes, stream>>>(m, a, p, tiles);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(64 + 128 * kEpiSplit), (size_t)p.smem_bytes, stream, m, a, p, tiles));
   return B200PETS_OK;
 }
 

@@ -83,6 +83,10 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
                "r"(r[3])
                : "memory");
 }
+// 32 lanes x 2 consecutive columns store
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint32_t (&r)[2]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
