@@ -30,7 +30,8 @@ struct TcPlan {
   int nblk[B200PETS_MAX_LAYERS];  // K-blocks (64 K-elements) per layer
   uint32_t stage_bytes;
   int nstages;
-  uint32_t off_A, off_ring, off_obs, off_act, off_const, off_cout, off_bar;
+  uint32_t off_A, off_ring, off_obs, off_act, off_tail, off_const, off_cout, off_bar;
+  int tail_ld;
   uint32_t tmem_cols;
   int obs_ld, act_ld;
   int h0n;  // columns of the first N half of the hidden layers
@@ -88,40 +89,29 @@ __device__ __forceinline__ uint32_t a_chunk_off(int i, int kc) { return (uint32_
 struct InDims {
   int Kp0, D, Dp, A, in, obs_process;
 };
-static __device__ __noinline__ void build_input_tmem(const InDims m, const float* my_obs, const float* arow,
-                                                     const float* c_mean, const float* c_istd, uint32_t a_out, int cs,
-                                                     int CS, uint64_t* bar_ar) {
+static __device__ __noinline__ void build_input_tmem(const InDims m, const float* my_obs, const float* tail,
+                                                     const float2* c_norm, uint32_t a_out, int cs, int CS,
+                                                     uint64_t* bar_ar) {
   const int Kp0 = m.Kp0;
   // Work unit = 8 operand columns (4 TMEM columns, one tcgen05.st.x4), dealt round-robin to the CS column-split warps
-  // of the row: with Kp0 = 32 every warp has exactly one unit.  c_mean / c_istd are Kp0 long ((0, 1) past the real
-  // inputs) and c_mean[Kp0 .. Kp0+2] = {1, 1, 0} is the source of the two bias-one columns and the zero pad, so every
-  // element is "load, subtract, scale" from a warp-uniform source pointer: the eight elements' loads are independent
-  // (the branchy form serialised ~8 x (3 dependent LDS + branches) ~ 1.3 k cycles on the step's critical path).
-  const float* c_one = c_mean + Kp0;
+  // of the row: with Kp0 = 32 every warp has exactly one unit.  Columns past the processed observation come from the
+  // row's `tail` words (this step's actions, the two bias ones, zero pad, already in operand order) and c_norm holds
+  // {mean, 1/std} pairs ((0, 1) past the real inputs), so every element is "load, subtract, scale" with independent
+  // loads (a branchy form serialised ~8 x (3 dependent LDS + branches) ~ 1.3 k cycles on the step's critical path).
   for (int gi = cs; gi < Kp0 / 8; gi += CS) {
-    float raw[8], mu[8], is[8];
-    if (m.obs_process == B200PETS_PROC_NONE) {
+    float raw[8];
+    float2 nm[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int j = gi * 8 + e;
-        const float* src = j < m.Dp ? my_obs + j : (j < m.in ? arow + (j - m.Dp) : c_one + min(j - m.in, 2));
-        raw[e] = *src;
-        mu[e] = c_mean[j];
-        is[e] = c_istd[j];
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {  // generic observation pre-processors (sin / cos columns): cold path
-        const int j = gi * 8 + e;
-        raw[e] = j < m.Dp ? proc_obs_elem(my_obs, j, m.obs_process)
-                          : (j < m.in ? arow[j - m.Dp] : c_one[min(j - m.in, 2)]);
-        mu[e] = c_mean[j];
-        is[e] = c_istd[j];
-      }
+    for (int e = 0; e < 8; ++e) {
+      const int j = gi * 8 + e;
+      if (m.obs_process == B200PETS_PROC_NONE) raw[e] = j < m.Dp ? my_obs[j] : tail[j - m.Dp];
+      else raw[e] = j < m.Dp ? proc_obs_elem(my_obs, j, m.obs_process) : tail[j - m.Dp];  // sin / cos columns: cold path
+      nm[e] = c_norm[j];
     }
     uint32_t pk[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16((raw[2 * e] - mu[2 * e]) * is[2 * e], (raw[2 * e + 1] - mu[2 * e + 1]) * is[2 * e + 1]);
+    for (int e = 0; e < 4; ++e)
+      pk[e] = pack_bf16((raw[2 * e] - nm[2 * e].x) * nm[2 * e].y, (raw[2 * e + 1] - nm[2 * e + 1].x) * nm[2 * e + 1].y);
     tmem_st4(a_out + (uint32_t)(4 * gi), pk);
   }
   tmem_st_wait();
@@ -273,18 +263,21 @@ static __device__ __noinline__ void cem_tail_refit(const TailArgs* ap, int dims,
 //
 // TMEM columns: [0, 256) accumulators (hidden: halves at 0 and h0n; output layer at 0), [256, 384) and [384, 512)
 // the two activation buffers (layer g reads buffer g & 1 and its epilogue writes buffer (g + 1) & 1).
-template <int ACT, int CS, bool CEMF>  // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
+template <int ACT, int CS, bool CEMF, bool TL>  // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
+                                                // TL: clock64 stamps (b200pets_debug_timeline); compiled out of production kernels --
+                                                // even predicated-off stamps cost issue slots in the issue-bound end-of-step phase
 __global__ void __launch_bounds__(64 + 128 * CS, 1)
 rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ RolloutArgs a, const __grid_constant__ TcPlan p,
                   const long long num_tiles) {
   constexpr int kEpiThreads = 128 * CS;
+  long long* const tl = TL ? a.timeline : nullptr;
   constexpr int kThreadsAll = 64 + kEpiThreads;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ring = smem + p.off_ring;
   float* obs_s = reinterpret_cast<float*>(smem + p.off_obs);
   float* act_s = reinterpret_cast<float*>(smem + p.off_act);
-  float* c_mean = reinterpret_cast<float*>(smem + p.off_const);
-  float* c_istd = c_mean + m.Kp[0] + 4;  // c_mean[Kp0 .. Kp0+2] = {1, 1, 0}: source of the bias-one / pad columns
+  float2* c_norm = reinterpret_cast<float2*>(smem + p.off_const);  // [Kp0] {mean, 1/std}; (0, 1) past the real inputs
+  float* tail_s = reinterpret_cast<float*>(smem + p.off_tail);      // [128][tail_ld]: operand columns Dp .. Kp0-1 per row
   // per-output constants of the output-layer epilogue, one 16-byte load per output (padded to a multiple of 4 outputs):
   //   x = max_logvar * log2(e), y = exp(max_logvar - min_logvar), z = exp(min_logvar / 2), w = 1 if the prediction is a
   //   delta to add to the old observation (0: keep the raw prediction -- no_delta columns, the learned-reward column, pad)
@@ -303,11 +296,11 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
   // staged model, which no kernel of a plan writes.
   pdl_trigger();
   if (CEMF) pdl_wait();  // the fused-CEM variants stage the sampling distribution in their prologue
-  if (a.timeline && threadIdx.x == 64 && (blockIdx.x == 0 || blockIdx.x == 40)) {
+  if (tl && threadIdx.x == 64 && (blockIdx.x == 0 || blockIdx.x == 40)) {
     long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    a.timeline[256 + (blockIdx.x ? 8 : 0) + 0] = clock64();  // kernel entry (cycles), wall clock (ns)
-    a.timeline[256 + (blockIdx.x ? 8 : 0) + 1] = gt;
+    tl[256 + (blockIdx.x ? 8 : 0) + 0] = clock64();  // kernel entry (cycles), wall clock (ns)
+    tl[256 + (blockIdx.x ? 8 : 0) + 1] = gt;
   }
 
   if (threadIdx.x == 0) {
@@ -321,14 +314,8 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
     mbar_init(&bar_acc[1], 1);
     mbar_fence_init();
   }
-  for (int j = threadIdx.x; j < m.in; j += kThreadsAll) {
-    c_mean[j] = m.norm_mode ? m.norm_mean_f[j] : 0.f;
-    c_istd[j] = m.norm_mode ? m.norm_istd_f[j] : 1.f;
-  }
-  for (int j = m.in + threadIdx.x; j < m.Kp[0] + 4; j += kThreadsAll) {
-    c_mean[j] = (j == m.Kp[0] || j == m.Kp[0] + 1) ? 1.f : 0.f;
-    if (j < m.Kp[0]) c_istd[j] = 1.f;
-  }
+  for (int j = threadIdx.x; j < m.Kp[0]; j += kThreadsAll)
+    c_norm[j] = (j < m.in && m.norm_mode) ? make_float2(m.norm_mean_f[j], m.norm_istd_f[j]) : make_float2(0.f, 1.f);
   // logvar clamp folded into two per-output constants (see the output-layer epilogue):
   //   var = exp(min + softplus(max - softplus(max - lv) - min)) = exp(min) * (1 + exp(max - min) / (1 + exp(max - lv)))
   float* cem_tab = reinterpret_cast<float*>(c_out + outq);  // [2][kCemTabDims]: sampling mean, sqrt(constrained variance) (fused CEM)
@@ -408,7 +395,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int t = a.t0; t < a.t1; ++t) {
           for (int l = 0; l < nlayers; ++l, ++g) {
-            const bool stamp = a.timeline && lane == 0 && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x;
+            const bool stamp = tl && lane == 0 && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x;
             const int nk = m.Kp[l] >> 4;
             const bool hidden = l < L;
             const uint32_t np = (uint32_t)m.Np[l];
@@ -423,12 +410,12 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             const uint32_t idesc0 = umma_idesc_bf16_m128((uint32_t)n0);
             const int ksplit = (l == 0) ? nk : min(nk, c0);  // K steps whose activations arrive with half 0
             const uint64_t b_inc = (uint64_t)((2u * b_lbo) >> 4);  // descriptor start-address step per K step
-            if (stamp) a.timeline[64 + l * 4 + 0] = clock64();
+            if (stamp) tl[64 + l * 4 + 0] = clock64();
             mbar_wait(slot_full, slot_phase);
             mbar_wait(&bar_ar[0], ar_par);
             if (!hidden && !final_early) mbar_wait(&bar_ar[1], ar_par);
             tc_fence_after();
-            if (stamp) a.timeline[64 + l * 4 + 1] = clock64();
+            if (stamp) tl[64 + l * 4 + 1] = clock64();
             uint64_t bdesc = umma_smem_desc(slot_addr, b_lbo, 128u);
             if (elect_one()) {
               uint64_t bd = bdesc;
@@ -469,7 +456,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             }
             __syncwarp();
             ar_par ^= 1u;
-            if (stamp) a.timeline[64 + l * 4 + 3] = clock64();
+            if (stamp) tl[64 + l * 4 + 3] = clock64();
           }
         }
       }
@@ -498,8 +485,9 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
 
     const InDims in_dims{m.Kp[0], m.D, m.Dp, m.A, m.in, m.obs_process};
-    auto build_input = [&](int tt) {
-      build_input_tmem(in_dims, my_obs, act_buf(tt), c_mean, c_istd, t_lane + 256u + ((g & 1u) << 7), cs,
+    float* my_tail = tail_s + i * p.tail_ld;  // [act (A) | 1 | 1 | 0 ..]: written with the actions of the step to be built
+    auto build_input = [&](int) {
+      build_input_tmem(in_dims, my_obs, my_tail, c_norm, t_lane + 256u + ((g & 1u) << 7), cs,
                        CS, bar_ar);
     };
 
@@ -555,20 +543,28 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
           const float* ap = act_row + (long long)a.t0 * a.act_t_stride;
           float* arow = act_buf(a.t0);
 #pragma unroll 1
-          for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
+          for (int j = 0; j < m.A; ++j) {
+            const float v = valid ? ap[j] : 0.f;
+            arow[j] = v;
+            my_tail[j] = v;
+          }
         }
+#pragma unroll 1
+        for (int j = m.A; j < in_dims.Kp0 - m.Dp; ++j) my_tail[j] = j < m.A + 2 ? 1.f : 0.f;  // bias ones, zero pad
       }
       if (CEMF && sampler) cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, a.seq0 + seq_n, a.t0, m.A,
                                       act_buf(a.t0), pop_row);
+      if (CEMF && sampler)
+        for (int j = 0; j < m.A; ++j) my_tail[j] = act_buf(a.t0)[j];
       epi_bar();
       build_input(a.t0);
 
       for (int t = a.t0; t < a.t1; ++t) {
-        const bool stamp = a.timeline && blockIdx.x == 0 && warp == 2 && lane == 0 && t == a.t0 + 5 && tile == blockIdx.x;
+        const bool stamp = tl && blockIdx.x == 0 && warp == 2 && lane == 0 && t == a.t0 + 5 && tile == blockIdx.x;
         int sp = 0;
-        if (stamp) a.timeline[sp++] = clock64();  // 0: step start (layer-0 operand already handed over)
-        if (a.timeline && warp == 2 && lane == 0 && tile == blockIdx.x && (blockIdx.x == 0 || blockIdx.x == 40) && t - a.t0 < 60)
-          a.timeline[128 + (blockIdx.x ? 64 : 0) + (t - a.t0)] = clock64();  // coarse: every step start of two CTAs
+        if (stamp) tl[sp++] = clock64();  // 0: step start (layer-0 operand already handed over)
+        if (tl && warp == 2 && lane == 0 && tile == blockIdx.x && (blockIdx.x == 0 || blockIdx.x == 40) && t - a.t0 < 60)
+          tl[128 + (blockIdx.x ? 64 : 0) + (t - a.t0)] = clock64();  // coarse: every step start of two CTAs
         const bool more = t + 1 < a.t1;
         if (owner && act_regs && more) {  // global loads complete under the layers (not in fused-CEM mode)
           const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
@@ -592,7 +588,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
               acc1_par ^= 1u;
             }
             tc_fence_after();
-            if (stamp) a.timeline[sp++] = clock64();  // accumulator half ready
+            if (stamp) tl[sp++] = clock64();  // accumulator half ready
             const int cbeg = h == 0 ? 0 : c0;
             const int cend = h == 0 ? c0 : (kp_next >> 4);
             for (int c = cbeg + cs; c < cend; c += CS) {
@@ -622,7 +618,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bar_ar[h]);
-            if (stamp) a.timeline[sp++] = clock64();  // activations of this half written
+            if (stamp) tl[sp++] = clock64();  // activations of this half written
           }
           // ---- side work in the gap while the next layer's first accumulator half completes ----
           if (l < 2) {  // this step's model noise: Philox + Box-Muller for output group g0 + l * CS
@@ -642,6 +638,8 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             if (CEMF && l == (L > 1 ? 1 : 0) && sampler && more)
               cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, a.seq0 + seq_n, t + 1,
                                  m.A, act_buf(t + 1), pop_row);
+            if (CEMF && l == (L > 1 ? 1 : 0) && sampler && more)
+              for (int j = 0; j < m.A; ++j) my_tail[j] = act_buf(t + 1)[j];
           } else if (l == 2 && owner && !cem) {
             if (!more) continue;
             // next step's actions -> the other action buffer (the one score(t - 1) just finished reading)
@@ -649,19 +647,28 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             if (act_regs) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                if (j < m.A) arow[j] = an[j];
+                if (j < m.A) {
+                  arow[j] = an[j];
+                  my_tail[j] = an[j];
+                }
             } else {
               const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
       #pragma unroll 1
-        for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
+        for (int j = 0; j < m.A; ++j) {
+                const float v = valid ? ap[j] : 0.f;
+                arow[j] = v;
+                my_tail[j] = v;
+              }
             }
           }
         }
         if (L < 3 && owner && more && !cem) {  // shallow models: the action hand-over did not fit in a gap above
           float* arow = act_buf(t + 1);
           const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
-  #pragma unroll 1
-        for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
+#pragma unroll 1
+          for (int j = 0; j < m.A; ++j) arow[j] = valid ? ap[j] : 0.f;
+          // (shallow models never take the fused path: the generic builder runs after the end-of-step barrier, and the
+          //  tail still holds this step's actions until then -- it is refreshed right before that builder call)
         }
 
         // ---- output layer: groups of 4 outputs; Gaussian sample, delta add-back (branch-free inner maths) ----
@@ -669,10 +676,10 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         acc0_par ^= 1u;
         ++g;
         tc_fence_after();
-        if (stamp) a.timeline[sp++] = clock64();  // output accumulator ready
+        if (stamp) tl[sp++] = clock64();  // output accumulator ready
         // the column split with the most output groups (cs = CS - 1: groups 0, CS, ..) bounds the end-of-step barrier
-        const bool stamp3 = a.timeline && blockIdx.x == 0 && warp == 2 + 4 * (CS - 1) && lane == 0 && t == a.t0 + 5 && tile == blockIdx.x;
-        if (stamp3) a.timeline[56] = clock64();
+        const bool stamp3 = tl && blockIdx.x == 0 && warp == 2 + 4 * (CS - 1) && lane == 0 && t == a.t0 + 5 && tile == blockIdx.x;
+        if (stamp3) tl[56] = clock64();
         // Slot gq = outputs [4 gq, 4 gq + 4) AND (fused mode) the next step's layer-0 operand columns [4 gq, 4 gq + 4).
         // Without an observation pre-processor input column j < D IS output j, so the thread that samples an output
         // also normalises it and writes it straight into the next step's A operand in TMEM (tcgen05.st.x2): no
@@ -683,7 +690,6 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         const bool fuse_in = more && m.obs_process == B200PETS_PROC_NONE && defer_score;
         const int nslots = fuse_in ? max(ngroups, in_dims.Kp0 >> 2) : ngroups;
         const uint32_t a_next = t_lane + 256u + ((g & 1u) << 7);  // A buffer of the next step's layer 0 (g already advanced)
-        const float* anext = act_buf(t + 1);
         for (int gq = CS - 1 - cs; gq < nslots; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
           const int u = (gq - (CS - 1 - cs)) / CS;
           float nw[4] = {0.f, 0.f, 0.f, 0.f};
@@ -692,7 +698,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
           tmem_ld4(t_lane + (uint32_t)(4 * gq), rm);
           if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rl);
           tmem_ld_wait();
-          if (stamp) a.timeline[40 + 4 * u] = clock64();
+          if (stamp) tl[40 + 4 * u] = clock64();
           // Branch-free per output: one 16-byte constant load, 3 MUFU (ex2, rcp, sqrt), one LDS + FADD/FSEL + STS of the state.
           //   var = exp(min + softplus(max - softplus(max - lv) - min)) = e^min * (1 + e^(max-min) / (1 + e^(max-lv)))
           //   (gaussian_mlp.py:150-153 folded into two per-output constants), pred = mean + sqrt(var) * z
@@ -713,7 +719,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
               philox_normal4((uint32_t)rid_glob, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z);
             }
           }
-          if (stamp) a.timeline[41 + 4 * u] = clock64();
+          if (stamp) tl[41 + 4 * u] = clock64();
           const float4* cg = c_out + 4 * gq;
           float* og = my_obs + 4 * gq;
 #pragma unroll
@@ -736,42 +742,55 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             og[2 * h] = nw[2 * h];
             og[2 * h + 1] = nw[2 * h + 1];
           }
-          if (stamp) a.timeline[42 + 4 * u] = clock64();
+          if (stamp) tl[42 + 4 * u] = clock64();
           }
           if (fuse_in && 4 * gq < in_dims.Kp0) {  // next step's operand columns 4 gq .. 4 gq + 3
+            if (stamp) tl[43 + 4 * u] = clock64();
             float x[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = 4 * gq + e;
-              const float raw = j < m.D ? nw[e] : (j < m.in ? anext[j - m.D] : c_mean[in_dims.Kp0 + min(j - m.in, 2)]);
-              x[e] = (raw - c_mean[j]) * c_istd[j];
+              const float tv = my_tail[max(j - m.D, 0)];  // next step's actions / bias ones / pad (unused for j < D)
+              const float2 nm = c_norm[j];
+              x[e] = ((j < m.D ? nw[e] : tv) - nm.x) * nm.y;
             }
             uint32_t pk[2] = {pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3])};
             tmem_st2(a_next + (uint32_t)(2 * gq), pk);
+            if (stamp) tl[48 + u] = clock64();
           }
         }
         if (fuse_in) {  // hand the operand to the MMA warp: both halves' barriers, as build_input_tmem does
+          if (stamp) tl[52] = clock64();
           tmem_st_wait();
+          if (stamp) tl[53] = clock64();
           tc_fence_before();
           mbar_arrive(&bar_ar[0]);
           mbar_arrive(&bar_ar[1]);
+          if (stamp) tl[54] = clock64();
         } else {
           tc_fence_before();
         }
-        if (stamp) a.timeline[sp++] = clock64();  // outputs sampled (fused mode: next input handed over)
-        if (stamp3) a.timeline[57] = clock64();
+        if (stamp) tl[sp++] = clock64();  // outputs sampled (fused mode: next input handed over)
+        if (stamp3) tl[57] = clock64();
         const bool score_now = scorer && !(more && defer_score);
         // the row's words are written by four warps: a barrier before anything reads the whole row (the generic input
         // builder, an immediate score).  In fused mode with deferred scoring nothing does until the next step's gaps,
         // which are ordered behind this point by the accumulator barriers.
         if (!fuse_in || !(more && defer_score)) epi_bar();
-        if (stamp) a.timeline[sp++] = clock64();  // barrier
-        if (more && !fuse_in) build_input(t + 1);  // generic path: next step's layer 0 starts while the owner scores this step
-        if (stamp) a.timeline[sp++] = clock64();  // next input handed over
-        if (stamp3) a.timeline[58] = clock64();
+        if (stamp) tl[sp++] = clock64();  // barrier
+        if (more && !fuse_in) {  // generic path: next step's layer 0 starts while the owner scores this step
+          if (L < 3) {  // shallow models handed the actions over after the last gap: copy them behind the barrier
+            if (owner)
+              for (int j = 0; j < m.A; ++j) my_tail[j] = act_buf(t + 1)[j];
+            epi_bar();
+          }
+          build_input(t + 1);
+        }
+        if (stamp) tl[sp++] = clock64();  // next input handed over
+        if (stamp3) tl[58] = clock64();
         // ---- reward, termination, accumulate: deferred into a gap of the next step when the model is deep enough ----
         if (score_now) score(t);
-        if (stamp) a.timeline[sp++] = clock64();  // reward done
+        if (stamp) tl[sp++] = clock64();  // reward done
       }
       // ---- store row state ----
       if (owner && a.store_state && valid && a.obs_out) {
@@ -787,11 +806,11 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
 
   tc_fence_before();
   __syncthreads();
-  if (a.timeline && threadIdx.x == 64 && (blockIdx.x == 0 || blockIdx.x == 40)) {
+  if (tl && threadIdx.x == 64 && (blockIdx.x == 0 || blockIdx.x == 40)) {
     long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    a.timeline[256 + (blockIdx.x ? 8 : 0) + 2] = clock64();  // all tiles of this CTA done
-    a.timeline[256 + (blockIdx.x ? 8 : 0) + 3] = gt;
+    tl[256 + (blockIdx.x ? 8 : 0) + 2] = clock64();  // all tiles of this CTA done
+    tl[256 + (blockIdx.x ? 8 : 0) + 3] = gt;
   }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
   // ---- fused CEM iteration: the last CTA to get here refits the sampling distribution ----
@@ -1073,7 +1092,10 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   p.off_A = 0;
   p.off_obs = off; off += (uint32_t)kTileM * p.obs_ld * 4;
   p.off_act = off; off += 3u * (uint32_t)kTileM * p.act_ld * 4;
-  p.off_const = off; off += (uint32_t)(2 * m.Kp[0] + 4) * 4;
+  p.tail_ld = (m.Kp[0] - m.Dp) | 1;
+  p.off_tail = off; off += (uint32_t)kTileM * p.tail_ld * 4;
+  off = (off + 15u) & ~15u;
+  p.off_const = off; off += (uint32_t)(2 * m.Kp[0]) * 4;
   off = (off + 15u) & ~15u;
   p.off_cout = off; off += (uint32_t)(4 * outq + 2 * kCemTabDims) * 4;
   off = (off + 15u) & ~15u;
@@ -1115,14 +1137,15 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
   void (*kern)(const ModelDev, const RolloutArgs, const TcPlan, const long long) = nullptr;
   switch (m.act) {
     case B200PETS_ACT_SILU:
-      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, true> : rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, false>;
+      if (a.timeline && !cemf) kern = rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, false, true>;  // the one instrumented variant
+      else kern = cemf ? rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, true, false> : rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, false, false>;
       break;
     case B200PETS_ACT_RELU:
-      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, true> : rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, false>;
+      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, true, false> : rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, false, false>;
       break;
     default:
-      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, true>
-                  : rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, false>;
+      kern = cemf ? rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, true, false>
+                  : rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, false, false>;
       break;
   }
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));

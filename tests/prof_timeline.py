@@ -19,7 +19,8 @@ lib.b200pets_debug_timeline(None)
 b = buf.cpu().tolist()
 t0 = b[0]
 print("epilogue thread stamps (cycles since step start):", [x - t0 for x in b[:24] if x])
-print("fine stamps:", [x - t0 for x in b[40:56] if x])
+print("fine stamps (slot u: 40+4u loads done, 41+4u noise ready, 42+4u state written, 43+4u operand part begins; 48+u operand stored; 52 before wait::st, 53 after, 54 arrived):",
+      {i: x - t0 for i, x in enumerate(b[40:56], start=40) if x})
 print("column split CS-1 (two output groups): output accumulator ready, groups done, next input handed over:", [x - t0 for x in b[56:59] if x])
 for l in range(5):
     s = b[64 + 4 * l: 68 + 4 * l]
