@@ -318,7 +318,8 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
     c_norm[j] = (j < m.in && m.norm_mode) ? make_float2(m.norm_mean_f[j], m.norm_istd_f[j]) : make_float2(0.f, 1.f);
   // logvar clamp folded into two per-output constants (see the output-layer epilogue):
   //   var = exp(min + softplus(max - softplus(max - lv) - min)) = exp(min) * (1 + exp(max - min) / (1 + exp(max - lv)))
-  float* cem_tab = reinterpret_cast<float*>(c_out + outq);  // [2][kCemTabDims]: sampling mean, sqrt(constrained variance) (fused CEM)
+  // [2][kCemTabDims]: sampling mean, sqrt(constrained variance): behind the weight ring, allocated for fused-CEM launches only
+  float* cem_tab = reinterpret_cast<float*>(smem + p.smem_bytes);
   __shared__ int sh_tail[2];
   for (int j = threadIdx.x; j < outq; j += kThreadsAll) {
     const bool real = j < m.out;
@@ -690,14 +691,22 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         const bool fuse_in = more && m.obs_process == B200PETS_PROC_NONE && defer_score;
         const int nslots = fuse_in ? max(ngroups, in_dims.Kp0 >> 2) : ngroups;
         const uint32_t a_next = t_lane + 256u + ((g & 1u) << 7);  // A buffer of the next step's layer 0 (g already advanced)
-        for (int gq = CS - 1 - cs; gq < nslots; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
+        // One slot.  rm / rl: this slot's mean / logvar accumulator words, already requested; rmn / rln: the registers the
+        // NEXT slot's words are requested into before this slot's maths, so that their TMEM round trip (~450 cycles under
+        // load) hides behind it.  Two register sets alternate (a tcgen05.ld destination must not be touched before the
+        // following tcgen05.wait::ld, so the sets are never copied).
+        auto ld_slot = [&](int gq, uint32_t (&rmx)[4], uint32_t (&rlx)[4]) {
+          if (gq < ngroups) {
+            tmem_ld4(t_lane + (uint32_t)(4 * gq), rmx);
+            if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rlx);
+          }
+        };
+        auto do_slot = [&](int gq, uint32_t (&rm)[4], uint32_t (&rl)[4], uint32_t (&rmn)[4], uint32_t (&rln)[4]) {
           const int u = (gq - (CS - 1 - cs)) / CS;
           float nw[4] = {0.f, 0.f, 0.f, 0.f};
           if (gq < ngroups) {
-          uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
-          tmem_ld4(t_lane + (uint32_t)(4 * gq), rm);
-          if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rl);
           tmem_ld_wait();
+          ld_slot(gq + CS, rmn, rln);
           if (stamp) tl[40 + 4 * u] = clock64();
           // Branch-free per output: one 16-byte constant load, 3 MUFU (ex2, rcp, sqrt), one LDS + FADD/FSEL + STS of the state.
           //   var = exp(min + softplus(max - softplus(max - lv) - min)) = e^min * (1 + e^(max-min) / (1 + e^(max-lv)))
@@ -757,6 +766,15 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             uint32_t pk[2] = {pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3])};
             tmem_st2(a_next + (uint32_t)(2 * gq), pk);
             if (stamp) tl[48 + u] = clock64();
+          }
+        };
+        {
+          uint32_t ra[4], la[4] = {0u, 0u, 0u, 0u}, rb[4], lb[4] = {0u, 0u, 0u, 0u};
+          int gq = CS - 1 - cs;  // reversed: the row owner (cs 0) gets the fewest groups
+          ld_slot(gq, ra, la);
+          for (; gq < nslots; gq += 2 * CS) {
+            do_slot(gq, ra, la, rb, lb);
+            if (gq + CS < nslots) do_slot(gq + CS, rb, lb, ra, la);
           }
         }
         if (fuse_in) {  // hand the operand to the MMA warp: both halves' barriers, as build_input_tmem does
@@ -1097,7 +1115,7 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   off = (off + 15u) & ~15u;
   p.off_const = off; off += (uint32_t)(2 * m.Kp[0]) * 4;
   off = (off + 15u) & ~15u;
-  p.off_cout = off; off += (uint32_t)(4 * outq + 2 * kCemTabDims) * 4;
+  p.off_cout = off; off += (uint32_t)(4 * outq) * 4;
   off = (off + 15u) & ~15u;
   p.off_bar = off; off += (2 * kMaxStages + 4) * 8 + 16;
   off = (off + 127u) & ~127u;
@@ -1148,8 +1166,11 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
                   : rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, false, false>;
       break;
   }
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-  CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(64 + 128 * kEpiSplit), (size_t)p.smem_bytes, stream, m, a, p, tiles));
+  const size_t smem_launch = (size_t)p.smem_bytes + (cemf ? (size_t)2 * kCemTabDims * sizeof(float) : 0);
+  if (smem_launch > (size_t)g_max_smem)
+    return b200pets_set_error(B200PETS_EUNSUPPORTED, "fused CEM iteration: no shared memory left for the sampling table");
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch));
+  CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(64 + 128 * kEpiSplit), smem_launch, stream, m, a, p, tiles));
   return B200PETS_OK;
 }
 
