@@ -691,22 +691,14 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         const bool fuse_in = more && m.obs_process == B200PETS_PROC_NONE && defer_score;
         const int nslots = fuse_in ? max(ngroups, in_dims.Kp0 >> 2) : ngroups;
         const uint32_t a_next = t_lane + 256u + ((g & 1u) << 7);  // A buffer of the next step's layer 0 (g already advanced)
-        // One slot.  rm / rl: this slot's mean / logvar accumulator words, already requested; rmn / rln: the registers the
-        // NEXT slot's words are requested into before this slot's maths, so that their TMEM round trip (~450 cycles under
-        // load) hides behind it.  Two register sets alternate (a tcgen05.ld destination must not be touched before the
-        // following tcgen05.wait::ld, so the sets are never copied).
-        auto ld_slot = [&](int gq, uint32_t (&rmx)[4], uint32_t (&rlx)[4]) {
-          if (gq < ngroups) {
-            tmem_ld4(t_lane + (uint32_t)(4 * gq), rmx);
-            if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rlx);
-          }
-        };
-        auto do_slot = [&](int gq, uint32_t (&rm)[4], uint32_t (&rl)[4], uint32_t (&rmn)[4], uint32_t (&rln)[4]) {
+        for (int gq = CS - 1 - cs; gq < nslots; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
           const int u = (gq - (CS - 1 - cs)) / CS;
           float nw[4] = {0.f, 0.f, 0.f, 0.f};
           if (gq < ngroups) {
+          uint32_t rm[4], rl[4] = {0u, 0u, 0u, 0u};
+          tmem_ld4(t_lane + (uint32_t)(4 * gq), rm);
+          if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rl);
           tmem_ld_wait();
-          ld_slot(gq + CS, rmn, rln);
           if (stamp) tl[40 + 4 * u] = clock64();
           // Branch-free per output: one 16-byte constant load, 3 MUFU (ex2, rcp, sqrt), one LDS + FADD/FSEL + STS of the state.
           //   var = exp(min + softplus(max - softplus(max - lv) - min)) = e^min * (1 + e^(max-min) / (1 + e^(max-lv)))
@@ -766,15 +758,6 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             uint32_t pk[2] = {pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3])};
             tmem_st2(a_next + (uint32_t)(2 * gq), pk);
             if (stamp) tl[48 + u] = clock64();
-          }
-        };
-        {
-          uint32_t ra[4], la[4] = {0u, 0u, 0u, 0u}, rb[4], lb[4] = {0u, 0u, 0u, 0u};
-          int gq = CS - 1 - cs;  // reversed: the row owner (cs 0) gets the fewest groups
-          ld_slot(gq, ra, la);
-          for (; gq < nslots; gq += 2 * CS) {
-            do_slot(gq, ra, la, rb, lb);
-            if (gq + CS < nslots) do_slot(gq + CS, rb, lb, ra, la);
           }
         }
         if (fuse_in) {  // hand the operand to the MMA warp: both halves' barriers, as build_input_tmem does
