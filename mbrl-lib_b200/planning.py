@@ -13,7 +13,6 @@
 """
 from __future__ import annotations
 
-import abc
 import ctypes as C
 import importlib
 import time
@@ -25,10 +24,19 @@ import torch
 from . import _lib
 
 
-class Agent(abc.ABC):  # mbrl/planning/core.py:18-49
-    @abc.abstractmethod
+# When mbrl-lib itself is importable (the drop-in case: a user's PETS script with mbrl installed), the classes below
+# derive from ITS plugin bases, so `isinstance(x, mbrl.planning.Agent)` / `issubclass(cls, Optimizer)` checks in user
+# code hold ("class X(mbrl.planning.Optimizer)").  Without it they stand alone.
+try:  # pragma: no cover - depends on the host environment
+    from mbrl.planning.core import Agent as _RefAgent
+    from mbrl.planning.trajectory_opt import Optimizer as _RefOptimizer
+except Exception:  # mbrl (or one of its own dependencies) is not installed
+    _RefAgent = _RefOptimizer = object
+
+
+class Agent(_RefAgent):  # mbrl/planning/core.py:18-49
     def act(self, obs: np.ndarray, **_kwargs) -> np.ndarray:
-        ...
+        raise NotImplementedError
 
     def plan(self, obs: np.ndarray, **_kwargs) -> np.ndarray:
         return self.act(obs, **_kwargs)
@@ -37,7 +45,7 @@ class Agent(abc.ABC):  # mbrl/planning/core.py:18-49
         pass
 
 
-class Optimizer:  # mbrl/planning/trajectory_opt.py:21-40
+class Optimizer(_RefOptimizer):  # mbrl/planning/trajectory_opt.py:21-40
     def __init__(self):
         pass
 

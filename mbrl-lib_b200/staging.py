@@ -31,8 +31,11 @@ def _activation_of(module) -> tuple:
 class StagedModel:
     """Owns the C handle of one staged model and re-stages it when the source object changed."""
 
-    def __init__(self, dynamics_model, reward_fn=None, termination_fn=None):
-        self.lib = _lib.load()
+    def __init__(self, dynamics_model, reward_fn=None, termination_fn=None, stage: bool = True):
+        """``stage=False`` only reads the source object (description, layer list, members, signature) and touches
+        neither the library nor a device: that is how the duck-typing contract is checked against real
+        ``mbrl.models`` objects on a CPU-only host (tests/test_reference_objects.py)."""
+        self.lib = _lib.load() if stage else None
         self.src = dynamics_model
         mlp = getattr(dynamics_model, "model", None)
         if mlp is None or not hasattr(mlp, "hidden_layers") or not hasattr(mlp, "mean_and_logvar"):
@@ -41,7 +44,7 @@ class StagedModel:
                 f"{type(dynamics_model).__name__}({type(mlp).__name__ if mlp is not None else None})")
         self.mlp = mlp
         dev = torch.device(mlp.mean_and_logvar.weight.device)
-        if dev.type != "cuda":
+        if stage and dev.type != "cuda":
             raise RuntimeError(f"b200pets runs on a CUDA device; the model lives on {dev} (no CPU fallback)")
         self.device = dev
         self.reward_id = functions.resolve_reward(reward_fn)
@@ -49,7 +52,8 @@ class StagedModel:
         self.handle: Optional[C.c_void_p] = None
         self._sig = None
         self._structure = None
-        self.ensure_fresh()
+        if stage:
+            self.ensure_fresh()
 
     # ---- description -----------------------------------------------------------------------------------
     def _layers(self) -> List:
@@ -129,8 +133,8 @@ class StagedModel:
             mx_np = np.ascontiguousarray(self.mlp.max_logvar.detach().float().cpu().numpy().reshape(-1))
             mn = mn_np.ctypes.data_as(C.POINTER(C.c_float))
             mx = mx_np.ctypes.data_as(C.POINTER(C.c_float))
-        stream = _lib.stream_ptr()
         with torch.cuda.device(self.device):
+            stream = _lib.stream_ptr()  # the model's device's current stream, not the caller's current device's
             if self.handle is not None and structure == self._structure:
                 _lib.check(self.lib.b200pets_model_refresh(self.handle, W, Bv, mem, nm, ns, mn, mx, stream), "model_refresh")
             else:
