@@ -116,8 +116,11 @@ static __device__ __noinline__ void build_input_tmem(const InDims m, const float
   }
   tmem_st_wait();
   tc_fence_before();
-  mbar_arrive(&bar_ar[0]);
-  mbar_arrive(&bar_ar[1]);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {  // one arrival per warp: the barriers count warps
+    mbar_arrive(&bar_ar[0]);
+    mbar_arrive(&bar_ar[1]);
+  }
 }
 
 // Actions of (sequence n, step t) drawn from the CEM sampling distribution with exactly the Philox keying of
@@ -285,7 +288,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
   float4* c_out = reinterpret_cast<float4*>(smem + p.off_cout);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* bar_empty = bar_full + kMaxStages;
-  uint64_t* bar_ar = bar_empty + kMaxStages;  // [2] activations of half h written (count: all epilogue threads)
+  uint64_t* bar_ar = bar_empty + kMaxStages;  // [2] activations of half h written (count: epilogue warps)
   uint64_t* bar_acc = bar_ar + 2;             // [2] accumulator of half h complete (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
 
@@ -308,8 +311,8 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    mbar_init(&bar_ar[0], kEpiThreads);
-    mbar_init(&bar_ar[1], kEpiThreads);
+    mbar_init(&bar_ar[0], kEpiThreads / 32);  // one arrival per epilogue warp
+    mbar_init(&bar_ar[1], kEpiThreads / 32);
     mbar_init(&bar_acc[0], 1);
     mbar_init(&bar_acc[1], 1);
     mbar_fence_init();
@@ -618,7 +621,8 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bar_ar[h]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_ar[h]);
             if (stamp) tl[sp++] = clock64();  // activations of this half written
           }
           // ---- side work in the gap while the next layer's first accumulator half completes ----
@@ -765,8 +769,11 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
           tmem_st_wait();
           if (stamp) tl[53] = clock64();
           tc_fence_before();
-          mbar_arrive(&bar_ar[0]);
-          mbar_arrive(&bar_ar[1]);
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&bar_ar[0]);
+            mbar_arrive(&bar_ar[1]);
+          }
           if (stamp) tl[54] = clock64();
         } else {
           tc_fence_before();
@@ -991,7 +998,7 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int k, int
     mbar_fence_init();
   }
   fence_proxy_async_smem();
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1001,7 +1008,7 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int k, int
     const uint32_t a0 = smem_u32(A_s), b0 = smem_u32(B_s);
     long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
-      for (int kk = 0; kk < (mode == 3 ? 0 : k / 16); ++kk) {
+      for (int kk = 0; kk < (mode >= 3 ? 0 : k / 16); ++kk) {
         uint64_t ad, bd;
         if (mode == 0) {
           ad = umma_smem_desc(a0 + (uint32_t)(2 * kk) * 2048u, 2048u, 128u);
@@ -1013,7 +1020,18 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int k, int
           ad = umma_smem_desc(a0 + (uint32_t)kk * 256u, 128u, (uint32_t)(k / 8) * 128u);
           bd = umma_smem_desc(b0 + (uint32_t)kk * 256u, 128u, (uint32_t)(k / 8) * 128u);
         }
-        if (mode != 3) umma_bf16_ss(tmem_base, ad, bd, idesc, 1u);
+        if (mode < 3) umma_bf16_ss(tmem_base, ad, bd, idesc, 1u);
+      }
+      if (mode == 4) {  // A-from-TMEM form (the rollout kernel's), tight issue loop
+        uint64_t bd = umma_smem_desc(b0, (uint32_t)n * 16u, 128u);
+        const uint64_t b_inc = (2u * (uint32_t)n * 16u) >> 4;
+        uint32_t acol = tmem_base + 256u;
+        const int nk = k / 16;
+        for (int kk = 0; kk < nk; ++kk) {
+          umma_bf16_ts(tmem_base, acol, bd, idesc, 1u);
+          acol += 8u;
+          bd += b_inc;
+        }
       }
       if (mode == 3) {  // tight issue: precomputed descriptors, start-address field advanced by a constant
         uint64_t ad = umma_smem_desc(a0, 2048u, 128u), bd = umma_smem_desc(b0, (uint32_t)n * 16u, 128u);
@@ -1037,7 +1055,119 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int k, int
   __syncthreads();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// micro-benchmark: the hidden-layer epilogue (tcgen05.ld x16 -> 16 x tanh.approx + FFMA -> bf16 pack -> tcgen05.st x8,
+// 13 chunks dealt to 4 column-split warps per lane quadrant, 16 warps) with / without MMAs running next to it.
+//   flags bit 0: MUFU + FFMA work, bit 1: TMEM loads / stores, bit 2: concurrent A-from-TMEM MMAs (M128 x n x 16,
+//   `nmma` of them, accumulating into columns [208, 208 + n): not the columns the epilogue reads), bit 3: the MMAs
+//   accumulate into the columns the epilogue reads (data is garbage either way: timing only), bit 4: the next chunk's
+//   tcgen05.ld is issued before this chunk's maths (software prefetch), bit 5 / 6 / 7: bf16 pack by integer round-half-up /
+//   integer round-to-nearest-even / no conversion instead of cvt.rn.bf16x2.f32 (F2FP).
+// out[0] = cycles of `reps` epilogue passes (warp 2), out[1] = cycles issue -> completion of the MMAs, out[2] = MMA issue only.
+// ---------------------------------------------------------------------------------------------------------
+template <int flags>
+__global__ void __launch_bounds__(64 + 512, 1) epi_bench_kernel(int nmma, int n, int reps, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 256 * 256 * 2 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 1) {
+    if ((flags & 4) && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)n);
+      const uint64_t bd0 = umma_smem_desc(smem_u32(smem), (uint32_t)n * 16u, 128u);
+      const uint64_t b_inc = (2u * (uint32_t)n * 16u) >> 4;
+      const uint32_t d = tmem_base + ((flags & 8) ? 0u : 208u);
+      long long t0 = clock64();
+      for (int i = 0; i < nmma; i += 12) {
+        uint64_t bd = bd0;
+        uint32_t acol = tmem_base + 416u;
+        for (int kk = 0; kk < 12 && i + kk < nmma; ++kk) {  // 96 activation columns = 12 K steps
+          umma_bf16_ts(d, acol, bd, idesc, 1u);
+          acol += 8u;
+          bd += b_inc;
+        }
+      }
+      long long t1 = clock64();
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      long long t2 = clock64();
+      out[1] = t2 - t0;
+      out[2] = t1 - t0;
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    const int q = warp & 3, cs = (warp - 2) >> 2;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    long long t0 = clock64();
+    float keep = 0.f;
+    for (int r = 0; r < reps; ++r) {
+      uint32_t nxt[16];
+      if ((flags & 2) && (flags & 16)) tmem_ld16(t_lane + (uint32_t)(16 * cs), nxt);
+      for (int c = cs; c < 13; c += 4) {
+        uint32_t r16[16];
+        if (flags & 2) {
+          if (flags & 16) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r16[e] = nxt[e];
+            if (c + 4 < 13) tmem_ld16(t_lane + (uint32_t)(16 * (c + 4)), nxt);
+          } else {
+            tmem_ld16(t_lane + (uint32_t)(16 * c), r16);
+            tmem_ld_wait();
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r16[e] = __float_as_uint(keep + (float)e);
+        }
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float x = __uint_as_float(r16[e]);
+          v[e] = (flags & 1) ? fmaf(x, tanh_approx(x), x) : x;
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (flags & 32) {  // round-half-up on the integer pipe + byte permute
+            pk[e] = __byte_perm(__float_as_uint(v[2 * e]) + 0x8000u, __float_as_uint(v[2 * e + 1]) + 0x8000u, 0x7632);
+          } else if (flags & 64) {  // round-to-nearest-even on the integer pipe
+            const uint32_t a0 = __float_as_uint(v[2 * e]), a1 = __float_as_uint(v[2 * e + 1]);
+            pk[e] = __byte_perm(a0 + 0x7FFFu + ((a0 >> 16) & 1u), a1 + 0x7FFFu + ((a1 >> 16) & 1u), 0x7632);
+          } else if (flags & 128) {  // no conversion at all
+            pk[e] = __float_as_uint(v[2 * e] + v[2 * e + 1]);
+          } else {
+            pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+          }
+        }
+        if ((flags & 2) && c < 12) tmem_st8(t_lane + 416u + (uint32_t)(8 * c), pk);
+        else keep += __uint_as_float(pk[0]);
+      }
+      if (flags & 2) tmem_st_wait();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+    long long t1 = clock64();
+    if (warp == 2 && lane == 0) out[0] = t1 - t0;
+    if (keep == 123.456f) out[3] = 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
@@ -1177,6 +1307,24 @@ int launch_umma_selftest(int k, int n, const float* a, const float* b, float* d,
 }
 
 int launch_umma_bench(int mode, int k, int n, int reps, long long* out, cudaStream_t stream) {
+  if (mode >= 100) {  // epilogue micro-benchmark: flags = mode - 100, k = number of concurrent MMAs, n = their N
+    if (n % 16 || n > 208 || n < 16) return b200pets_set_error(B200PETS_EINVAL, "epi_bench: bad n");
+    size_t smem_e = (size_t)256 * 256 * 2 + 1024;
+    void (*kern)(int, int, int, long long*) = nullptr;
+    switch (mode - 100) {  // compile-time flag sets: a run-time test per element would dominate what is being measured
+#define EPI_CASE(F) case F: kern = epi_bench_kernel<F>; break;
+      EPI_CASE(0) EPI_CASE(1) EPI_CASE(2) EPI_CASE(3) EPI_CASE(4) EPI_CASE(7) EPI_CASE(19) EPI_CASE(23)
+      EPI_CASE(32) EPI_CASE(33) EPI_CASE(34) EPI_CASE(35) EPI_CASE(39) EPI_CASE(51) EPI_CASE(55)
+      EPI_CASE(64) EPI_CASE(65) EPI_CASE(66) EPI_CASE(67) EPI_CASE(71)
+      EPI_CASE(128) EPI_CASE(129) EPI_CASE(130) EPI_CASE(131) EPI_CASE(135)
+#undef EPI_CASE
+      default: return b200pets_set_error(B200PETS_EINVAL, "epi_bench: flag set %d not instantiated", mode - 100);
+    }
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+    kern<<<1, 64 + 512, smem_e, stream>>>(k, n, reps, out);
+    CUDA_TRY(cudaGetLastError());
+    return B200PETS_OK;
+  }
   if (k % 16 || n % 16 || n > 256 || k > 256) return b200pets_set_error(B200PETS_EINVAL, "umma_bench: bad shape");
   size_t smem = (size_t)(128 + 256) * 256 * 2 + 1024;
   CUDA_TRY(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
