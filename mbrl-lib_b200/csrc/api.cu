@@ -343,7 +343,6 @@ static int eval_rows(b200pets_model_t model, const b200pets_rollout_cfg* cfg, co
   a.obs0 = obs0;
   a.total_state = total; a.dead_state = dead;
   int precision = cfg->precision;
-  if (cfg->propagation == B200PETS_PROP_EXPECTATION && precision == B200PETS_PREC_BF16_TC) precision = B200PETS_PREC_F32;
 
   const bool ts1 = cfg->propagation == B200PETS_PROP_RANDOM_MODEL;
   if (ts1 && perms) {
@@ -417,7 +416,6 @@ int b200pets_step(b200pets_model_t model, int32_t precision, int32_t propagation
   } else {
     a.slot_mode = 1;
   }
-  if (propagation == B200PETS_PROP_EXPECTATION && precision == B200PETS_PREC_BF16_TC) precision = B200PETS_PREC_F32;
   return dispatch(model, precision, a, (cudaStream_t)stream_);
 }
 

@@ -36,6 +36,9 @@ struct TcPlan {
   int obs_ld, act_ld;
   int h0n;  // columns of the first N half of the hidden layers
   uint32_t smem_bytes;
+  uint32_t off_exp;  // [128][exp_ld] member sums of mean / log2-variance terms (propagation "expectation" launches only)
+  int exp_ld;
+  int tail_split;  // fast tail chunk: 1 = two columns per column-split warp, 0 = one warp takes all eight
 };
 
 namespace {
@@ -54,6 +57,11 @@ __device__ __forceinline__ float tanh_approx(float x) {
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -266,7 +274,9 @@ static __device__ __noinline__ void cem_tail_refit(const TailArgs* ap, int dims,
 //
 // TMEM columns: [0, 256) accumulators (hidden: halves at 0 and h0n; output layer at 0), [256, 384) and [384, 512)
 // the two activation buffers (layer g reads buffer g & 1 and its epilogue writes buffer (g + 1) & 1).
-template <int ACT, int CS, bool CEMF, bool TL>  // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
+template <int ACT, int CS, bool CEMF, bool TL, bool EXP = false>  // EXP: propagation "expectation" (member passes); its own
+                                                // instantiation -- compiled into the production kernel it cost 64 B of spills
+                                                // CEMF: fused-CEM features compiled in (in-kernel sampling, last-CTA refit)
                                                 // TL: clock64 stamps (b200pets_debug_timeline); compiled out of production kernels --
                                                 // even predicated-off stamps cost issue slots in the issue-bound end-of-step phase
 __global__ void __launch_bounds__(64 + 128 * CS, 1)
@@ -349,9 +359,13 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const bool shuffle = a.slot_mode >= 1;
+  // propagation "expectation" (gaussian_mlp.py:213-215): every row through every member, mean and clamped logvar averaged
+  // over the members: `passes` = M forward passes per horizon step over the same layer-0 operand, member = pass
+  constexpr bool expect = EXP;
+  const int passes = expect ? m.M : 1;
+  const bool shuffle = a.slot_mode >= 1 && !expect;
   const ShuffleGeom geom = shuffle_geom(a.seq0, a.N, a.n_glob);
-  const long long Bm = shuffle ? 0 : a.B / m.M;
+  const long long Bm = shuffle ? 0 : (expect ? a.B : a.B / m.M);
   const int tpm = shuffle ? 1 : (int)((Bm + kTileM - 1) / kTileM);
   const int nlayers = p.nlayers;
   const int L = nlayers - 1;         // index of the output layer
@@ -367,9 +381,10 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int member = shuffle ? 0 : (int)(tile / tpm);
-        for (int t = a.t0; t < a.t1; ++t) {
-          const int mem = shuffle ? shuffle_member(a.seed, a.offset, a.slot_mode, shuffle_global_group(geom, tile), t, m.M) : member;
+        const int member = (shuffle || expect) ? 0 : (int)(tile / tpm);
+        for (int t = a.t0; t < a.t1; ++t)
+        for (int pass = 0; pass < passes; ++pass) {
+          const int mem = expect ? pass : (shuffle ? shuffle_member(a.seed, a.offset, a.slot_mode, shuffle_global_group(geom, tile), t, m.M) : member);
           const uint8_t* base = m.img + (size_t)(blockIdx.x % m.img_replicas) * m.img_replica_stride + (size_t)mem * m.img_member_stride;
           for (int l = 0; l < nlayers; ++l) {
             // one ring slot holds the whole layer image (K core columns contiguous): one barrier, one wait per layer
@@ -397,7 +412,8 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
       uint32_t g = 0;  // global layer counter: selects the activation buffer
       const uint32_t ring_addr = smem_u32(ring);
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int t = a.t0; t < a.t1; ++t) {
+        for (int tp = (a.t1 - a.t0) * passes; tp > 0; --tp) {
+          const int t = a.t1 - (tp + passes - 1) / passes;  // (only the timeline stamps look at it)
           for (int l = 0; l < nlayers; ++l, ++g) {
             const bool stamp = tl && lane == 0 && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x;
             const int nk = m.Kp[l] >> 4;
@@ -435,6 +451,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
               mbar_wait(&bar_ar[1], ar_par);
               tc_fence_after();
             }
+            if (stamp) tl[64 + l * 4 + 2] = clock64();
             if (elect_one()) {
               uint64_t bd = bdesc + (uint64_t)ksplit * b_inc;
               uint32_t acol = a_col + 8u * (uint32_t)ksplit;
@@ -485,7 +502,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
     const bool draw = !m.deterministic && a.sample;
     // scoring of step t may be deferred into the gap after hidden layer 2 of step t + 1 only if another hidden layer
     // follows that gap: the output-layer epilogue (which overwrites obs / learned reward) then needs this thread first
-    const bool defer_score = L >= 4;
+    const bool defer_score = L >= 4 && !expect;
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
 
     const InDims in_dims{m.Kp[0], m.D, m.Dp, m.A, m.in, m.obs_process};
@@ -495,6 +512,17 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
                        CS, bar_ar);
     };
 
+    // tail chunk of a hidden layer's activations: columns [16 c_tail, Kp) = (hid % 16) real ones, the two bias ones, zero pad
+    const int c_tail = (NpH >> 4) - 1;
+    const int hid_true = m.N[0];
+    const bool fast_tail = L >= 1 && CS == 4 && hid_true - 16 * c_tail == 8 && hid_true >= m.Kp[0];  // (layer-0 operand words stay below)
+    if (fast_tail && cs == 0) {  // tail_const_init: words [hid / 2, Np / 2) of both activation buffers = {1 1}, 0, 0, 0
+      const uint32_t kc[4] = {0x3F803F80u, 0u, 0u, 0u};
+      tmem_st4(t_lane + 256u + (uint32_t)(hid_true >> 1), kc);
+      tmem_st4(t_lane + 384u + (uint32_t)(hid_true >> 1), kc);
+      tmem_st_wait();
+      tc_fence_before();
+    }
     pdl_wait();  // actions / observation / row state are the previous kernels' outputs; ours are written after this
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       bool valid;
@@ -577,6 +605,10 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         }
         float zpre0[4] = {0.f, 0.f, 0.f, 0.f}, zpre1[4] = {0.f, 0.f, 0.f, 0.f};  // statically indexed: registers
 
+        // propagation "expectation": one forward pass per member over the same layer-0 operand; everything that belongs to
+        // the step and not to a member (noise draw, action hand-over, state update, scoring) happens in the first / last pass
+        for (int pass = 0; pass < passes; ++pass) {
+        const bool last_pass = pass == passes - 1;
         // ---- hidden layers: accumulator half -> activation -> bf16 pairs -> next layer's A operand in TMEM ----
         for (int l = 0; l < L; ++l, ++g) {
           const int n_true = m.N[l];
@@ -585,8 +617,10 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h == 0) {
+              if (TL && tl && lane == 0 && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x) tl[400 + (warp - 2) * 16 + l * 4 + 1] = clock64();
               mbar_wait(&bar_acc[0], acc0_par);
               acc0_par ^= 1u;
+              if (TL && tl && lane == 0 && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x) tl[400 + (warp - 2) * 16 + l * 4 + 2] = clock64();
             } else {
               mbar_wait(&bar_acc[1], acc1_par);
               acc1_par ^= 1u;
@@ -595,7 +629,8 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             if (stamp) tl[sp++] = clock64();  // accumulator half ready
             const int cbeg = h == 0 ? 0 : c0;
             const int cend = h == 0 ? c0 : (kp_next >> 4);
-            for (int c = cbeg + cs; c < cend; c += CS) {
+            const int cend_whole = (fast_tail && h == 1) ? c_tail : cend;  // the tail chunk has its own fast form below
+            for (int c = cbeg + cs; c < cend_whole; c += CS) {
               float v[16];
               if (16 * c < NpH) {
                 uint32_t r[16];
@@ -619,16 +654,42 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
               for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
               tmem_st8(a_out + (uint32_t)(8 * c), pk);
             }
+            if (fast_tail && h == 1) {
+              // Tail chunk, fast form: only its 8 real columns are activated and stored.  The two bias-one columns and the zero
+              // pad behind them sit in activation words that no layer ever changes: written once per CTA (tail_const_init).
+              // The generic form (the `col == n_true` selects above) costs ~800 cycles more per layer: 32 compare + select
+              // pairs chained through three predicate registers on the one warp whose arrival the next layer's MMAs wait
+              // for (profiles/r2_timeline_per_warp.txt).
+              if (p.tail_split) {  // two columns per column-split warp: tcgen05.ld.x2, 2 MUFU, one packed word
+                uint32_t r2[2];
+                tmem_ld2(t_lane + (uint32_t)(16 * c_tail + 2 * cs), r2);
+                tmem_ld_wait();
+                tmem_st1(a_out + (uint32_t)(8 * c_tail + cs),
+                         pack_bf16(act_tc<ACT>(__uint_as_float(r2[0]), m.leaky), act_tc<ACT>(__uint_as_float(r2[1]), m.leaky)));
+              } else if (cs == (c_tail - cbeg) % CS) {  // the warp whose turn it is: tcgen05.ld.x8, 8 MUFU, tcgen05.st.x4
+                uint32_t r8[8];
+                tmem_ld8(t_lane + (uint32_t)(16 * c_tail), r8);
+                tmem_ld_wait();
+                uint32_t pk4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  pk4[e] = pack_bf16(act_tc<ACT>(__uint_as_float(r8[2 * e]), m.leaky), act_tc<ACT>(__uint_as_float(r8[2 * e + 1]), m.leaky));
+                tmem_st4(a_out + (uint32_t)(8 * c_tail), pk4);
+              }
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_ar[h]);
+            if (TL && tl && lane == 0 && blockIdx.x == 0 && t == a.t0 + 5 && tile == blockIdx.x) tl[400 + (warp - 2) * 16 + l * 4 + (h == 0 ? 3 : 0)] = clock64();
             if (stamp) tl[sp++] = clock64();  // activations of this half written
           }
           // ---- side work in the gap while the next layer's first accumulator half completes ----
           if (l < 2) {  // this step's model noise: Philox + Box-Muller for output group g0 + l * CS
+            // (measured: spreading the four warps' draws over more gaps, two per gap, made the step 2 % slower -- the second
+            //  gap then holds two draws plus nothing to hide them under; profiles/README.md)
             const int gq = (CS - 1 - cs) + l * CS;
-            if (draw && !a.eps && gq < ngroups) {
+            if (pass == 0 && draw && !a.eps && gq < ngroups) {
               float z4[4];
               philox_normal4((uint32_t)rid_glob, (uint32_t)t, RNG_STREAM_EPS | (uint32_t)gq, (uint32_t)a.offset, a.seed, z4);
 #pragma unroll
@@ -640,12 +701,12 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             // previous step's reward / termination, off the critical path (the scorer thread has no noise group here)
             if (l == 1 && scorer && t > a.t0 && defer_score) score(t - 1);
             // fused CEM: next step's actions are drawn here by the row's sampler thread (third action buffer)
-            if (CEMF && l == (L > 1 ? 1 : 0) && sampler && more)
+            if (CEMF && l == (L > 1 ? 1 : 0) && sampler && more && last_pass)
               cem_sample_actions(a.seed, a.cem_offset, a.cem_clipped, a.cem_lb, a.cem_ub, cem_tab, cem_tab + kCemTabDims, a.seq0 + seq_n, t + 1,
                                  m.A, act_buf(t + 1), pop_row);
-            if (CEMF && l == (L > 1 ? 1 : 0) && sampler && more)
+            if (CEMF && l == (L > 1 ? 1 : 0) && sampler && more && last_pass)
               for (int j = 0; j < m.A; ++j) my_tail[j] = act_buf(t + 1)[j];
-          } else if (l == 2 && owner && !cem) {
+          } else if (l == 2 && owner && !cem && last_pass) {  // (earlier passes still need this step's actions in the tail)
             if (!more) continue;
             // next step's actions -> the other action buffer (the one score(t - 1) just finished reading)
             float* arow = act_buf(t + 1);
@@ -667,7 +728,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             }
           }
         }
-        if (L < 3 && owner && more && !cem) {  // shallow models: the action hand-over did not fit in a gap above
+        if (L < 3 && owner && more && !cem && last_pass) {  // shallow models: the action hand-over did not fit in a gap above
           float* arow = act_buf(t + 1);
           const float* ap = act_row + (long long)(t + 1) * a.act_t_stride;
 #pragma unroll 1
@@ -692,7 +753,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         // the outputs carry the action / bias-one / pad columns.  Pre-processed observations keep the generic builder.
         // (L >= 4: the next step's actions, written in the gap after hidden layer 2, must be ordered before this point
         //  by one more accumulator barrier -- the same condition that lets the score be deferred.)
-        const bool fuse_in = more && m.obs_process == B200PETS_PROC_NONE && defer_score;
+        const bool fuse_in = more && m.obs_process == B200PETS_PROC_NONE && defer_score;  // (never with "expectation")
         const int nslots = fuse_in ? max(ngroups, in_dims.Kp0 >> 2) : ngroups;
         const uint32_t a_next = t_lane + 256u + ((g & 1u) << 7);  // A buffer of the next step's layer 0 (g already advanced)
         for (int gq = CS - 1 - cs; gq < nslots; gq += CS) {  // reversed: the row owner (cs 0) gets the fewest groups
@@ -704,6 +765,30 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
           if (!m.deterministic) tmem_ld4(t_lane + (uint32_t)(m.outp + 4 * gq), rl);
           tmem_ld_wait();
           if (stamp) tl[40 + 4 * u] = clock64();
+          // "expectation": member sums of the mean and of log2(1 + e2) (the clamped logvar is min + ln(1 + e2), see below)
+          // in the row's scratch words; the last pass turns them into the averaged mean and sqrt(exp(averaged logvar))
+          float sdv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (expect) {
+            float* exm = reinterpret_cast<float*>(smem + p.off_exp) + i * p.exp_ld + 4 * gq;
+            float* exl = exm + outq;
+            const float inv_m = 1.0f / (float)passes;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 ce = c_out[4 * gq + e];
+              float l2 = 0.f;
+              if (draw) {
+                const float e1 = ex2_approx(fmaf(__uint_as_float(rl[e]), -1.4426950408889634f, ce.x));
+                l2 = lg2_approx(1.f + ce.y * rcp_approx(1.f + e1));
+              }
+              const float am = (pass ? exm[e] : 0.f) + __uint_as_float(rm[e]);
+              const float al = (pass ? exl[e] : 0.f) + l2;
+              exm[e] = am;
+              exl[e] = al;
+              rm[e] = __float_as_uint(am * inv_m);
+              sdv[e] = ce.z * ex2_approx(0.5f * al * inv_m);  // sqrt(exp(min + ln2 * mean_m log2(1 + e2)))
+            }
+            if (!last_pass) continue;
+          }
           // Branch-free per output: one 16-byte constant load, 3 MUFU (ex2, rcp, sqrt), one LDS + FADD/FSEL + STS of the state.
           //   var = exp(min + softplus(max - softplus(max - lv) - min)) = e^min * (1 + e^(max-min) / (1 + e^(max-lv)))
           //   (gaussian_mlp.py:150-153 folded into two per-output constants), pred = mean + sqrt(var) * z
@@ -737,7 +822,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
               const float e10 = ex2_approx(fmaf(__uint_as_float(rl[2 * h]), -1.4426950408889634f, c0.x));
               const float e11 = ex2_approx(fmaf(__uint_as_float(rl[2 * h + 1]), -1.4426950408889634f, c1.x));
               const float e20 = c0.y * rcp_approx(1.f + e10), e21 = c1.y * rcp_approx(1.f + e11);
-              const float sd0 = c0.z * sqrt_approx(1.f + e20), sd1 = c1.z * sqrt_approx(1.f + e21);
+              const float sd0 = expect ? sdv[2 * h] : c0.z * sqrt_approx(1.f + e20), sd1 = expect ? sdv[2 * h + 1] : c1.z * sqrt_approx(1.f + e21);
               p0 = fmaf(sd0, z[2 * h], p0);
               p1 = fmaf(sd1, z[2 * h + 1], p1);
             }
@@ -763,6 +848,11 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
             tmem_st2(a_next + (uint32_t)(2 * gq), pk);
             if (stamp) tl[48 + u] = clock64();
           }
+        }
+        if (!last_pass) {  // next member: same observation, same actions, through the generic builder (it arrives on both barriers)
+          tc_fence_before();
+          build_input(t);
+          continue;
         }
         if (fuse_in) {  // hand the operand to the MMA warp: both halves' barriers, as build_input_tmem does
           if (stamp) tl[52] = clock64();
@@ -799,6 +889,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
         // ---- reward, termination, accumulate: deferred into a gap of the next step when the model is deep enough ----
         if (score_now) score(t);
         if (stamp) tl[sp++] = clock64();  // reward done
+        }  // passes
       }
       // ---- store row state ----
       if (owner && a.store_state && valid && a.obs_out) {
@@ -1188,7 +1279,7 @@ static int tc_device_limits() {  // cached per device (a process may drive sever
 }
 
 // smem plan for a model; returns false when the tensor-core path does not cover the dimensions
-bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
+bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out, bool expectation = false) {
   TcPlan p{};
   p.nlayers = m.L + 1;
   if (m.in + 2 > 256 || m.hid + 2 > 256 || m.nout > 256 || m.D > 256) return false;
@@ -1204,18 +1295,20 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   p.stage_bytes = (stage + 127u) & ~127u;
   p.tmem_cols = 512;
   (void)tm;
-  // N split of the hidden layers (16-column chunks): half 0 takes ~9/13 of them.  After half 1's activations arrive only
-  // the K steps that read them (4 of 13 at width 208) are left before half 0's accumulator of the next layer completes,
-  // and half 1's shorter epilogue still covers the next layer's first 9 K steps (measured: 208 -> 144 + 64).
+  // N split of the hidden layers (16-column chunks): half 0 takes ~8/13 of them (width 208: 128 + 80 columns).  An MMA costs
+  // max(65, N / 2) cycles per K step (profiles/r2_umma_issue_rate_ts.txt), so 128 + 80 is 130 cycles per K step where
+  // 144 + 64 was 137; every column-split warp gets exactly two chunks of half 0, one of half 1 and a slice of the tail chunk.
   {
     const int C = m.Np[0] / 16;
-    int c0 = (C * 9 + 6) / 13;
+    int c0 = (C * 8 + 6) / 13;
     static const int c0_env = [] { const char* e = getenv("B200PETS_TC_H0CHUNKS"); return e ? atoi(e) : 0; }();  // A/B switch
     if (c0_env > 0) c0 = c0_env;
     c0 = max(1, min(C - 1, c0));
     p.h0n = c0 * 16;
   }
   if (m.Np[0] - p.h0n < 16) return false;
+  static const int ts_env = [] { const char* e = getenv("B200PETS_TC_TAILSPLIT"); return e ? atoi(e) : 0; }();  // A/B switch
+  p.tail_split = ts_env;
   const int outq = (m.out + 3) & ~3;
   p.obs_ld = max(m.D, outq) | 1;  // a row holds the D observation words, the learned-reward word and the output padding
   p.act_ld = m.A | 1;
@@ -1229,6 +1322,10 @@ bool tc_make_plan(const ModelDev& m, int max_smem, TcPlan* out) {
   p.off_const = off; off += (uint32_t)(2 * m.Kp[0]) * 4;
   off = (off + 15u) & ~15u;
   p.off_cout = off; off += (uint32_t)(4 * outq) * 4;
+  off = (off + 15u) & ~15u;
+  p.off_exp = off;
+  p.exp_ld = (2 * outq) | 1;
+  if (expectation) off += (uint32_t)kTileM * p.exp_ld * 4;
   off = (off + 15u) & ~15u;
   p.off_bar = off; off += (2 * kMaxStages + 4) * 8 + 16;
   off = (off + 127u) & ~127u;
@@ -1250,14 +1347,15 @@ bool tc_supported(const ModelDev& m) {
 int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stream) {
   int rc = tc_device_limits();
   if (rc) return rc;
-  if (a.propagation == B200PETS_PROP_EXPECTATION)
-    return b200pets_set_error(B200PETS_EUNSUPPORTED, "tensor-core path does not cover propagation='expectation'");
+  const bool expect = a.propagation == B200PETS_PROP_EXPECTATION;
   TcPlan p;
-  if (!tc_make_plan(m, g_max_smem, &p))
+  if (!tc_make_plan(m, g_max_smem, &p, expect))
     return b200pets_set_error(B200PETS_EUNSUPPORTED, "model dimensions outside the tensor-core path (in %d hid %d out %d)",
                               m.in, m.hid, m.out);
   long long tiles;
-  if (a.slot_mode >= 1) {
+  if (expect) {  // every row through every member: plain 128-row tiles, no member binding
+    tiles = (a.B + kTileM - 1) / kTileM;
+  } else if (a.slot_mode >= 1) {
     tiles = (long long)a.P * shuffle_geom(a.seq0, a.N, a.n_glob).C_loc;
   } else {
     long long Bm = a.B / m.M;
@@ -1266,6 +1364,12 @@ int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stre
   const unsigned grid = (unsigned)min((long long)g_sm_count, tiles);
   const bool cemf = a.cem_mu != nullptr || a.tail_counter != nullptr;
   void (*kern)(const ModelDev, const RolloutArgs, const TcPlan, const long long) = nullptr;
+  if (expect && cemf) return b200pets_set_error(B200PETS_EUNSUPPORTED, "fused CEM iteration does not cover propagation='expectation'");
+  if (expect) {
+    kern = m.act == B200PETS_ACT_SILU   ? rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, false, false, true>
+           : m.act == B200PETS_ACT_RELU ? rollout_tc_kernel<B200PETS_ACT_RELU, kEpiSplit, false, false, true>
+                                        : rollout_tc_kernel<B200PETS_ACT_LEAKY_RELU, kEpiSplit, false, false, true>;
+  } else
   switch (m.act) {
     case B200PETS_ACT_SILU:
       if (a.timeline && !cemf) kern = rollout_tc_kernel<B200PETS_ACT_SILU, kEpiSplit, false, true>;  // the one instrumented variant

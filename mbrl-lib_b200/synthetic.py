@@ -116,6 +116,10 @@ _register(CaseSpec("relu_expectation", obs_dim=11, act_dim=3, hid_size=64, num_l
                    elites=None, activation="relu", propagation="expectation", normalize=None,
                    reward_fn="inverted_pendulum", term_fn="inverted_pendulum",
                    population=24, horizon=6, particles=4))
+# expectation propagation at the headline model shape (7 members / 5 elites, 4 x 200 SiLU, fp64 normaliser), continuous reward:
+# the tensor-core kernel's member-pass path is pinned to the reference at the exact bars
+_register(CaseSpec("silu_expectation", obs_dim=17, act_dim=6, propagation="expectation",
+                   population=25, horizon=6, particles=4))
 _register(CaseSpec("hopper_tsinf", obs_dim=11, act_dim=3, hid_size=96, num_layers=3, ensemble_size=4,
                    elites=(3, 1), activation="silu", propagation="fixed_model", normalize="float64",
                    learned_rewards=True, reward_fn=None, term_fn="hopper",

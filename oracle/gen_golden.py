@@ -305,7 +305,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
     for nm in ["cartpole", "halfcheetah", "halfcheetah_small", "pets_halfcheetah_small", "humanoid_trunc",
-               "relu_expectation", "hopper_tsinf", "cartpole_pets", "pusher_det", "walker_ant", "humanoid_v4", "tc_hid64", "tc_wide", "tc_shallow", "ant_learned_fn"]:
+               "relu_expectation", "silu_expectation", "hopper_tsinf", "cartpole_pets", "pusher_det", "walker_ant", "humanoid_v4", "tc_hid64", "tc_wide", "tc_shallow", "ant_learned_fn"]:
         gen_rollout(nm)
     gen_step("mbpo_halfcheetah_small", 1000)
     gen_step("cartpole", 500)

@@ -9,7 +9,7 @@ spec, arrays, env = bench.build_problem("cuda:0")
 inp = syn.make_rollout_inputs(spec, with_noise=False)
 acts = torch.from_numpy(inp["actions"]).to("cuda:0")
 lib = _lib.load()
-buf = torch.zeros(512, dtype=torch.int64, device="cuda:0")
+buf = torch.zeros(1024, dtype=torch.int64, device="cuda:0")
 for _ in range(3):
     env.evaluate_action_sequences(acts, inp["obs0"], spec.particles)
 lib.b200pets_debug_timeline(_lib.ptr(buf))
@@ -24,7 +24,12 @@ print("fine stamps (slot u: 40+4u loads done, 41+4u noise ready, 42+4u state wri
 print("column split CS-1 (two output groups): output accumulator ready, groups done, next input handed over:", [x - t0 for x in b[56:59] if x])
 for l in range(5):
     s = b[64 + 4 * l: 68 + 4 * l]
-    print(f"mma layer {l}: starts waiting {s[0]-t0}, weights + first activation half ready {s[1]-t0}, all MMAs issued {s[3]-t0}")
+    print(f"mma layer {l}: starts waiting {s[0]-t0}, weights + first activation half ready {s[1]-t0}, second half seen {s[2]-t0}, all MMAs issued {s[3]-t0}")
+
+print("per epilogue warp (q, cs), hidden layer l: h1 arrived(l-1 -> this row shows l's own), reached acc0 wait, passed it, h0 arrived")
+for w in range(16):
+    row = b[400 + 16 * w: 416 + 16 * w]
+    print(f"  warp q{w % 4} cs{w // 4}: " + "  ".join(f"l{l}: wait@{row[4*l+1]-t0} pass@{row[4*l+2]-t0} h0@{row[4*l+3]-t0} h1@{row[4*l]-t0}" for l in range(4)))
 
 for name, base, kb in (("CTA 0", 128, 256), ("CTA 40", 192, 264)):
     st = [x for x in b[base:base + 60] if x]

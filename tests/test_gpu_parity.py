@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
 CONTINUOUS = ["halfcheetah_small", "pets_halfcheetah_small", "humanoid_trunc", "cartpole_pets", "pusher_det", "halfcheetah",
-              "humanoid_v4", "tc_hid64", "tc_wide", "tc_shallow"]
+              "humanoid_v4", "tc_hid64", "tc_wide", "tc_shallow", "silu_expectation"]
 DISCRETE = ["cartpole", "relu_expectation", "hopper_tsinf", "walker_ant", "ant_learned_fn"]
 
 
@@ -134,7 +134,7 @@ def test_rollout_f32_discrete_rewards(golden_dir, name):
 
 
 @pytest.mark.parametrize("name", ["halfcheetah_small", "pets_halfcheetah_small", "humanoid_trunc", "cartpole_pets",
-                                  "pusher_det", "halfcheetah", "tc_hid64", "tc_wide", "tc_shallow"])
+                                  "pusher_det", "halfcheetah", "tc_hid64", "tc_wide", "tc_shallow", "silu_expectation"])
 def test_rollout_tc_matches_oracle(golden_dir, name):
     spec, arrays, env = make_env(name, "bf16_tc")
     inp = syn.make_rollout_inputs(spec)
@@ -144,7 +144,7 @@ def test_rollout_tc_matches_oracle(golden_dir, name):
     assert_close_continuous(got, gold["returns"], 2e-2)
 
 
-@pytest.mark.parametrize("name", ["cartpole", "hopper_tsinf", "walker_ant", "ant_learned_fn"])
+@pytest.mark.parametrize("name", ["cartpole", "hopper_tsinf", "walker_ant", "ant_learned_fn", "relu_expectation"])
 def test_rollout_tc_discrete_rewards(golden_dir, name):
     spec, arrays, env = make_env(name, "bf16_tc")
     inp = syn.make_rollout_inputs(spec)
