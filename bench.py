@@ -205,7 +205,10 @@ def run_ours(args):
 
         def step():
             return opt.optimize(obj, x0=x0)
-        launches_per_step = 1 + CEM_ITERS * 3  # init + (sample, rollout, refit incl. particle mean) per iteration
+        if os.environ.get("B200PETS_CEM_MERGED", "1") == "0":
+            launches_per_step = 1 + CEM_ITERS * 3  # init + (sample, rollout, refit incl. particle mean) per iteration
+        else:  # init, first population, then per iteration: rollout + ONE refit-and-next-population kernel
+            launches_per_step = 2 + CEM_ITERS * 2
     else:
         from mbrl_lib_b200.dist import ShardedCEMOptimizer
 

@@ -15,6 +15,12 @@ int launch_rollout_f32(const ModelDev& m, const RolloutArgs& a, cudaStream_t str
 int launch_rollout_tc(const ModelDev& m, const RolloutArgs& a, cudaStream_t stream);
 int launch_umma_selftest(int k, int n, const float* a, const float* b, float* d, cudaStream_t stream);
 int launch_particle_mean(int N, int P, const float* total, float* returns, cudaStream_t stream);
+bool cem_refit_sample_supported(int population, int dims, int elite_num);
+int launch_cem_refit_sample(int population, int dims, int elite_num, float alpha, int use_std, const float* row_totals,
+                            int particles, float* values, float* mu, float* dispersion, float* best_value, float* best_solution,
+                            void* workspace, size_t workspace_bytes, int refit, int sample, const float* lb, const float* ub,
+                            const float* z_next, unsigned long long seed, unsigned long long offset, int clipped, int seq0,
+                            unsigned int* flag, unsigned int tag, float* pop, void* stream);
 int launch_cem_update_rows(int population, int dims, int elite_num, float alpha, int unbiased, int use_std,
                            const float* population_in, const float* row_totals, int particles, float* values, float* mu,
                            float* dispersion, float* best_value, float* best_solution, void* workspace,
@@ -429,6 +435,7 @@ __global__ void cem_init_kernel(int dims, const float* __restrict__ x0, const fl
   if (d == 0) {
     *best_value = -INFINITY;
     *reinterpret_cast<unsigned int*>(best_value + 1) = 0u;  // tail counter of the fused iteration kernel
+    *reinterpret_cast<unsigned int*>(best_value + 2) = 0u;  // "refit done" tag of cem_refit_sample_kernel
   }
   if (d >= dims) return;
   mu[d] = x0[d];
@@ -481,7 +488,40 @@ int b200pets_cem_plan(b200pets_model_t model, const b200pets_rollout_cfg* rcfg, 
                     model->desc.reward_fn != B200PETS_REWARD_EXTERNAL && model->desc.term_fn != B200PETS_TERM_EXTERNAL;
   const char* env_sik = getenv("B200PETS_CEM_SAMPLE_IN_KERNEL");
   const bool sample_in_kernel = env_sik && env_sik[0] == '1';
+  // Default: 2 launches per iteration -- rollout, then ONE kernel that refits (particle mean + top-k + mean / variance) and
+  // draws the next iteration's population (cem.cu cem_refit_sample_kernel); the first population comes from the same
+  // kernel in sample-only mode.  B200PETS_CEM_MERGED=0 (or a population outside the single-CTA refit) keeps the three
+  // separate kernels.
+  static const bool merged_env = [] { const char* e = getenv("B200PETS_CEM_MERGED"); return !(e && e[0] == '0'); }();
+  const bool merged = merged_env && !fuse && cem_refit_sample_supported(N, dims, ccfg->elite_num);
+  unsigned int* refit_flag = reinterpret_cast<unsigned int*>(best_val + 2);
+  auto next_pop = [&](int it_next, int refit, const float* totals) -> int {  // refit of it_next - 1 (if any) + population of it_next
+    const int sample = it_next < ccfg->num_iterations;
+    const unsigned long long off = rcfg->offset * 1024 + (unsigned long long)it_next;
+    return launch_cem_refit_sample(N, dims, ccfg->elite_num, ccfg->alpha, ccfg->clipped_normal, totals, P, values, mu, disp,
+                                   best_val, best_sol, upd_ws, upd_bytes, refit, sample, lower, upper,
+                                   (z && sample) ? z + (size_t)it_next * N * dims : nullptr, rng_key(rcfg->seed, off), off,
+                                   ccfg->clipped_normal, rcfg->first_sequence, refit_flag, (unsigned int)it_next, pop, stream);
+  };
+  if (merged) {
+    int rc0 = next_pop(0, 0, nullptr);
+    if (rc0) return rc0;
+  }
   for (int it = 0; it < ccfg->num_iterations; ++it) {
+    if (merged) {
+      b200pets_rollout_cfg rc_it = *rcfg;
+      rc_it.offset = rcfg->offset * 1024 + it;
+      const int nperm = rcfg->propagation == B200PETS_PROP_FIXED_MODEL ? 1 : H;
+      float* totals = nullptr;
+      int rc = eval_rows(model, &rc_it, obs0, pop, perms ? perms + (size_t)it * nperm * B : nullptr,
+                         eps ? eps + (size_t)it * H * B * model->desc.out_size : nullptr, nullptr, eval_ws, eval_bytes, stream,
+                         &totals);
+      if (rc) return rc;
+      rc = next_pop(it + 1, 1, totals);
+      if (rc) return rc;
+      if (values_out) CUDA_TRY(cudaMemcpyAsync(values_out + (size_t)it * N, values, sizeof(float) * N, cudaMemcpyDeviceToDevice, stream));
+      continue;
+    }
     if (fuse) {
       // default: population drawn by cem_sample_kernel, rollout + refit in one kernel (2 launches per iteration);
       // B200PETS_CEM_SAMPLE_IN_KERNEL=1 also draws the population inside the rollout kernel (1 launch per iteration,

@@ -11,16 +11,11 @@ namespace {
 // ------------------------------------------------------------------------------------------------------
 // sampling
 // ------------------------------------------------------------------------------------------------------
-__global__ void cem_sample_kernel(int n, int dims, const float* __restrict__ mu, const float* __restrict__ disp,
-                                  const float* __restrict__ lb, const float* __restrict__ ub,
-                                  const float* __restrict__ z, unsigned long long seed, unsigned long long offset,
-                                  int clipped, float* __restrict__ pop, int seq0) {
-  pdl_trigger();
-  pdl_wait();  // mu / disp come from the previous refit; pop may still be read by the previous iteration's kernels
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)n * dims) return;
+// one element of the population (trajectory_opt.py:110-128): idx = sequence * dims + d
+__device__ __forceinline__ float cem_sample_element(long long idx, int dims, float m, float dp, float lo, float hi,
+                                                    const float* __restrict__ z, unsigned long long seed,
+                                                    unsigned long long offset, int clipped, int seq0) {
   const int d = (int)(idx % dims);
-  const float m = mu[d], dp = disp[d], lo = lb[d], hi = ub[d];
   float zz;
   if (z) {
     zz = z[idx];
@@ -48,7 +43,19 @@ __global__ void cem_sample_kernel(int n, int dims, const float* __restrict__ mu,
     const float cv = fminf(mv, dp);
     v = zz * sqrtf(cv) + m;
   }
-  pop[idx] = v;
+  return v;
+}
+
+__global__ void cem_sample_kernel(int n, int dims, const float* __restrict__ mu, const float* __restrict__ disp,
+                                  const float* __restrict__ lb, const float* __restrict__ ub,
+                                  const float* __restrict__ z, unsigned long long seed, unsigned long long offset,
+                                  int clipped, float* __restrict__ pop, int seq0) {
+  pdl_trigger();
+  pdl_wait();  // mu / disp come from the previous refit; pop may still be read by the previous iteration's kernels
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * dims) return;
+  const int d = (int)(idx % dims);
+  pop[idx] = cem_sample_element(idx, dims, mu[d], disp[d], lb[d], ub[d], z, seed, offset, clipped, seq0);
 }
 
 // iCEM coloured noise: one thread per (sequence, action dim) synthesises the H samples of its series
@@ -408,8 +415,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) cem_select_kernel(const SelArg
 // are then computed from the per-row totals of the rollout kernel.  Same selection rule as cem_select_kernel (NaN ->
 // -1e-10, top-k by value, ties -> lowest index, elite_idx ascending); mean / variance are summed per coordinate over the
 // elites in ascending index order (a fixed order: the refit is bit-identical however the population was sharded).
-__global__ void __launch_bounds__(kSelThreads, 1)
-cem_select_small_kernel(const SelArgs s, const float* __restrict__ row_totals, int P) {
+static __device__ __forceinline__ void select_small_body(const SelArgs& s, const float* __restrict__ row_totals, int P) {
   extern __shared__ float esm[];  // [k][dims] elite rows
   __shared__ float sv[kSmallN];
   __shared__ unsigned char sf[kSmallN];
@@ -417,8 +423,6 @@ cem_select_small_kernel(const SelArgs s, const float* __restrict__ row_totals, i
   __shared__ int sh_best;
   const int tid = threadIdx.x;
   const int n = s.n, k = s.k, dims = s.dims;
-  pdl_trigger();
-  pdl_wait();  // values / row totals / population are the previous kernels' outputs
   for (int i = tid; i < n; i += kSelThreads) {
     float v;
     if (row_totals) {
@@ -497,6 +501,60 @@ cem_select_small_kernel(const SelArgs s, const float* __restrict__ row_totals, i
     }
   }
   if (better && tid == 0) *s.best_value = bv;
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+cem_select_small_kernel(const SelArgs s, const float* __restrict__ row_totals, int P) {
+  pdl_trigger();
+  pdl_wait();  // values / row totals / population are the previous kernels' outputs
+  select_small_body(s, row_totals, P);
+}
+
+// Refit of iteration i AND the population of iteration i + 1 in one launch (2 launches per CEM iteration: rollout, this).
+// CTA 0 runs the refit above and then publishes a tag; the other CTAs of the (small, co-resident: <= 64 CTAs, CTA 0 is
+// dispatched first) grid spin on it, then every CTA draws its slice of the next population from the new (mu, dispersion).
+// refit = 0: sample only (the first iteration's population); sample = 0: refit only (the last iteration).
+struct NextPop {
+  int refit, sample;
+  const float* lb;
+  const float* ub;
+  const float* z;  // injected noise of the NEXT iteration or NULL
+  unsigned long long seed, offset;
+  int clipped, seq0;
+  unsigned int* flag;
+  unsigned int tag;
+  float* pop_out;
+};
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+cem_refit_sample_kernel(const SelArgs s, const float* __restrict__ row_totals, int P, const NextPop q) {
+  pdl_trigger();
+  pdl_wait();
+  if (q.refit) {
+    if (blockIdx.x == 0) {
+      select_small_body(s, row_totals, P);
+      __syncthreads();  // every read of the old population (elite rows, best row) is done
+      if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(q.flag), "r"(q.tag) : "memory");
+      }
+    } else {
+      if (threadIdx.x == 0) {
+        unsigned int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q.flag) : "memory");
+        } while (v != q.tag);
+      }
+      __syncthreads();
+    }
+  }
+  if (!q.sample) return;
+  const long long tot = (long long)s.n * s.dims;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % s.dims);
+    q.pop_out[idx] = cem_sample_element(idx, s.dims, __ldcg(s.mu + d), __ldcg(s.disp + d), q.lb[d], q.ub[d], q.z, q.seed, q.offset,
+                                        q.clipped, q.seq0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -761,6 +819,39 @@ int launch_cem_update_rows(int population, int dims, int elite_num, float alpha,
                     row_totals, particles);
 }
 
+
+bool cem_refit_sample_supported(int population, int dims, int elite_num) {
+  return population <= kSmallN && (size_t)elite_num * dims * sizeof(float) <= 150 * 1024 && elite_num >= 2 && elite_num <= population;
+}
+
+// refit (particle mean fused, rows = per-particle totals) + next population; returns B200PETS_EUNSUPPORTED when the population
+// is outside the single-CTA refit (the caller then uses the separate kernels)
+int launch_cem_refit_sample(int population, int dims, int elite_num, float alpha, int use_std, const float* row_totals,
+                            int particles, float* values, float* mu, float* dispersion, float* best_value, float* best_solution,
+                            void* workspace, size_t workspace_bytes, int refit, int sample, const float* lb, const float* ub,
+                            const float* z_next, unsigned long long seed, unsigned long long offset, int clipped, int seq0,
+                            unsigned int* flag, unsigned int tag, float* pop, void* stream) {
+  const int n = population, k = elite_num;
+  if (!(n <= kSmallN && (size_t)k * dims * sizeof(float) <= 150 * 1024)) return B200PETS_EUNSUPPORTED;
+  if (refit && (k < 2 || k > n)) return b200pets_set_error(B200PETS_EINVAL, "cem_update: need 2 <= elite_num (%d) <= population (%d)", k, n);
+  if (workspace_bytes < b200pets_cem_update_workspace_bytes(n, dims, k)) return b200pets_set_error(B200PETS_EINVAL, "cem_update: workspace too small");
+  SelArgs s{};
+  s.n = n; s.dims = dims; s.k = k; s.alpha = alpha; s.unbiased = 1; s.use_std = use_std; s.mode = 0;
+  s.pop = pop; s.pstride = dims; s.values = values; s.vstride = 1; s.mu = mu; s.disp = dispersion;
+  s.best_value = best_value; s.best_solution = best_solution;
+  s.partial = reinterpret_cast<float*>(workspace);
+  s.elite_idx = reinterpret_cast<int*>(reinterpret_cast<float*>(workspace) + 33 * (size_t)dims);
+  NextPop q{};
+  q.refit = refit; q.sample = sample; q.lb = lb; q.ub = ub; q.z = z_next; q.seed = seed; q.offset = offset;
+  q.clipped = clipped; q.seq0 = seq0; q.flag = flag; q.tag = tag; q.pop_out = pop;
+  const long long tot = (long long)n * dims;
+  unsigned grid = sample ? (unsigned)min((long long)64, (tot + kSelThreads - 1) / kSelThreads) : 1u;
+  if (grid < 1) grid = 1;
+  const size_t esm = (size_t)k * dims * sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(cem_refit_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+  CUDA_TRY(launch_pdl(cem_refit_sample_kernel, dim3(grid), dim3(kSelThreads), esm, (cudaStream_t)stream, s, row_totals, particles, q));
+  return B200PETS_OK;
+}
 
 int launch_particle_mean(int N, int P, const float* total, float* returns, cudaStream_t stream) {
   particle_mean_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, P, total, returns);

@@ -814,6 +814,7 @@ rollout_tc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Ro
           float* og = my_obs + 4 * gq;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two outputs at a time: loads up front so that the two chains overlap
+            if (h == 1 && 4 * gq + 2 >= m.out) continue;  // pure padding pair (17 outputs: group 4 holds one real output)
             const float4 c0 = cg[2 * h], c1 = cg[2 * h + 1];
             const float o0 = og[2 * h], o1 = og[2 * h + 1];
             float p0 = __uint_as_float(rm[2 * h]), p1 = __uint_as_float(rm[2 * h + 1]);

@@ -132,7 +132,7 @@ class ShardedCEMOptimizer:
             self.last_values = torch.empty(self.num_iterations, n_loc, device=dev)
         if fused is not None:
             env = fused.model_env
-            env.staged.ensure_fresh()
+            env._fresh()
             prop = env._propagation()
             H = shape[0]
             # the same (seed, offset) on every rank: draws are keyed by GLOBAL sequence / row / group indices

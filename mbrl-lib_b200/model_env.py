@@ -40,6 +40,7 @@ class ModelEnv:
         self._ws: Optional[torch.Tensor] = None
         self._obs_pin: Optional[torch.Tensor] = None
         self._obs_dev: Optional[torch.Tensor] = None
+        self._auto_refresh = True  # re-check the staged copy's signature on every call (see hand_off_from)
 
     # ---- helpers ---------------------------------------------------------------------------------------
     def _propagation(self) -> str:
@@ -118,10 +119,53 @@ class ModelEnv:
         assert (assign >= 0).all()
         return torch.from_numpy(assign)
 
+    # ---- weight hand-off from training --------------------------------------------------
+    def _fresh(self):
+        if self._auto_refresh:
+            self.staged.ensure_fresh()
+
+    def push_weights(self):
+        """Re-stage the packed device copy NOW (fp32 gather of the elite members + bf16 UMMA images, a few small kernels on
+        the model's stream): what the end of ``ModelTrainer.train`` / ``set_elite`` / ``update_normalizer`` should call."""
+        self.staged.ensure_fresh()
+
+    def hand_off_from(self, trainer, model=None):
+        """Make training PUSH its result instead of every ``act()`` / ``step()`` polling for it.
+
+        ``trainer`` is the reference's ``mbrl.models.ModelTrainer`` (model_trainer.py:70-214): its ``train`` ends by loading
+        the best weights and calling ``model.set_elite`` (:205-214, 288-296), and the training loop of PETS / MBPO calls
+        ``update_normalizer`` right before it (mbrl/util/common.py:385-389).  ``train`` is wrapped so that the packed copy
+        is re-staged once, when it returns; the dynamics model's ``update_normalizer`` / ``set_elite`` (callable on their
+        own) are wrapped the same way.  From then on the planner's hot path no longer walks the parameters' version
+        counters (``_auto_refresh`` off): one signature walk per training round instead of one per planned action.
+        ``model`` defaults to this environment's dynamics model.  Returns ``trainer``."""
+        env = self
+        model = model if model is not None else self.dynamics_model
+
+        def _wrap(obj, name):
+            fn = getattr(obj, name, None)
+            if fn is None or getattr(fn, "_b200pets_pushes", False):
+                return
+            def pushed(*a, **kw):
+                out = fn(*a, **kw)
+                env.staged.ensure_fresh()
+                return out
+            pushed._b200pets_pushes = True
+            pushed.__wrapped__ = fn
+            setattr(obj, name, pushed)
+
+        if trainer is not None:
+            _wrap(trainer, "train")
+        for name in ("update_normalizer", "set_elite", "load"):
+            _wrap(model, name)
+        self.staged.ensure_fresh()
+        self._auto_refresh = False
+        return trainer
+
     # ---- reference API ---------------------------------------------------------------------------------
     def reset(self, initial_obs_batch: np.ndarray, return_as_np: bool = True) -> Dict[str, torch.Tensor]:
         assert len(initial_obs_batch.shape) == 2  # batch, obs_dim  (model_env.py:78-79)
-        self.staged.ensure_fresh()
+        self._fresh()
         obs = torch.from_numpy(np.ascontiguousarray(initial_obs_batch.astype(np.float32))).to(self.device)
         state = {"obs": obs, "propagation_indices": None}
         if self._propagation() == "fixed_model":
@@ -137,7 +181,7 @@ class ModelEnv:
              _perm: Optional[torch.Tensor] = None, _eps: Optional[torch.Tensor] = None, _offset: Optional[int] = None,
              _out=None):
         assert len(actions.shape) == 2  # batch, action_dim  (model_env.py:108)
-        self.staged.ensure_fresh()
+        self._fresh()
         with torch.no_grad():
             if isinstance(actions, np.ndarray):
                 actions = torch.from_numpy(actions).to(self.device)
@@ -200,7 +244,7 @@ class ModelEnv:
             assert initial_state.ndim in (1, 3)  # model_env.py:169
             if initial_state.ndim != 1:
                 raise NotImplementedError("pixel observations are outside the GaussianMLP hot path")
-            self.staged.ensure_fresh()
+            self._fresh()
             d = self.staged.desc
             if d.reward_fn == _lib.REWARD["external"] or d.term_fn == _lib.TERM["external"]:
                 return self._evaluate_stepwise(action_sequences, initial_state, num_particles)

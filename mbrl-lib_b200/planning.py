@@ -146,7 +146,7 @@ class CEMOptimizer(Optimizer):
 
     def _optimize_fused(self, obj: _FusedObjective, x0, noise, model_noise) -> torch.Tensor:
         env = obj.model_env
-        env.staged.ensure_fresh()
+        env._fresh()
         H, A = x0.shape
         prop = env._propagation()
         perms = eps = None

@@ -249,3 +249,58 @@ def test_our_model_env_on_real_reference_model_matches_reference_model_env(name,
         assert frac <= 0.02, f"{frac:.3f} of sequences differ"
     else:
         np.testing.assert_allclose(got, want, atol=tol * scale, rtol=0)
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_training_pushes_weights_to_the_planner():
+    """after ModelEnv.hand_off_from(trainer), the reference's own ModelTrainer.train (Adam steps in place,
+    best weights loaded back, set_elite; model_trainer.py:70-214, 288-296) leaves the packed device copy fresh WITHOUT any
+    polling by act() / step(), and the planner evaluates exactly what the reference evaluates on the trained weights."""
+    import mbrl_lib_b200 as bp
+    from mbrl.types import TransitionBatch
+    from mbrl.util.replay_buffer import BootstrapIterator, TransitionIterator
+
+    dev = "cuda:0"
+    spec, arrays, ref_env = _real_model("halfcheetah_small", dev)
+    wrapper = ref_env.dynamics_model
+    env = bp.ModelEnv(ref_env, wrapper, ref_env.termination_fn, ref_env.reward_fn, generator=torch.Generator(device=dev),
+                      precision="f32", ts1="perms")
+    trainer = mbrl.models.ModelTrainer(wrapper, optim_lr=1e-3, weight_decay=5e-5)
+    env.hand_off_from(trainer)
+    assert env._auto_refresh is False and env.staged._sig == env.staged._signature()
+
+    rng = np.random.default_rng(3)
+    n = 256
+    obs = rng.standard_normal((n, spec.obs_dim)).astype(np.float32)
+    act = rng.uniform(-1, 1, (n, spec.act_dim)).astype(np.float32)
+    nxt = (obs + 0.1 * rng.standard_normal((n, spec.obs_dim))).astype(np.float32)
+    data = TransitionBatch(obs, act, nxt, rng.standard_normal(n).astype(np.float32), np.zeros(n, bool), np.zeros(n, bool))
+    wrapper.update_normalizer(data)  # wrapped: pushes
+    assert env.staged._sig == env.staged._signature()
+    sig0 = env.staged._sig
+    train_it = BootstrapIterator(data, 64, spec.ensemble_size, shuffle_each_epoch=True, rng=rng)
+    val_it = TransitionIterator(data, 64)
+    trainer.train(train_it, dataset_val=val_it, num_epochs=2, silent=True)
+    # the weights moved (Adam, in place), the elite list was re-ranked by validation score, and the copy followed -- pushed
+    assert env.staged._sig != sig0
+    assert env.staged._sig == env.staged._signature(), "training did not push its weights"
+    assert env.staged.members() == list(wrapper.model.elite_models)
+
+    inp = syn.make_rollout_inputs(spec)
+    acts = torch.from_numpy(inp["actions"]).to(dev)
+    perms = torch.from_numpy(inp["perms"]).to(dev)
+    eps = torch.from_numpy(inp["eps"]).to(dev)
+    with _Feed([perms[t] for t in range(perms.shape[0])], [eps[t] for t in range(spec.horizon)]):
+        want = ref_env.evaluate_action_sequences(acts, inp["obs0"], spec.particles).float().cpu().numpy()
+    calls = {"n": 0}
+    real = env.staged.ensure_fresh
+
+    def counting():
+        calls["n"] += 1
+        return real()
+
+    env.staged.ensure_fresh = counting
+    got = env.evaluate_action_sequences(acts, inp["obs0"], spec.particles, _perms=perms, _eps=eps).cpu().numpy()
+    assert calls["n"] == 0, "the hot path still polls the parameters"
+    np.testing.assert_allclose(got, want, atol=2e-4 * max(1.0, float(np.abs(want).max())), rtol=0)
