@@ -217,7 +217,11 @@ def run_ours(args):
 
         def step():
             return opt.optimize(obj, x0=x0)
-        launches_per_step = CEM_ITERS * 5  # sample, rollout, particle mean, local top-k, refit-from-records (+ 1 NCCL kernel)
+        if os.environ.get("B200PETS_PEER_EXCHANGE", "1") != "0":
+            # first population, then per iteration: rollout, particle mean, values push, global select + elite push + refit + next population
+            launches_per_step = 1 + CEM_ITERS * 4
+        else:
+            launches_per_step = CEM_ITERS * 5  # sample, rollout, particle mean, local top-k, refit-from-records (+ 1 NCCL kernel)
 
     def barrier():
         if world > 1:
@@ -328,7 +332,7 @@ def run_ours(args):
         extras["population_scan_rollout_only"] = scan
         extras["config4_mbpo_step"] = mbpo_step_extra(device, flush)
     # ---- config 5: fixed GLOBAL population sharded over the ranks (strong scaling), collective share of an iteration ----
-    if world > 1:
+    if world > 1 and not args.no_scan5:
         from mbrl_lib_b200.dist import ShardedCEMOptimizer
 
         scan5 = []
@@ -357,8 +361,9 @@ def run_ours(args):
             del o5
         extras["config5_population_scan_sharded"] = {
             "what": "full 5-iteration plan, global population fixed and sharded over the ranks (strong scaling in N); "
-                    "collective = NCCL all-gather of local top-k records, timed with CUDA events around it (includes waiting "
-                    "for the slowest rank)", "rows": scan5}
+                    "collective = the exchange of the iteration, timed with CUDA events around it (includes waiting for the slowest "
+                    "rank): peer-memory path = values push + global select + elite push + refit + next population (two kernels); "
+                    "B200PETS_PEER_EXCHANGE=0 = NCCL all-gather of local top-k records only", "rows": scan5}
     clocks = sampler.stop() if rank == 0 else None
 
     cpu = None
@@ -507,6 +512,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-scan5", action="store_true", help="skip the sharded config-5 population scan (N > 1)")
     ap.add_argument("--no-scan", action="store_true", help="skip the population scan / extra configurations")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -235,6 +235,33 @@ int b200pets_cem_update_from_records(int32_t num_records, int32_t dims, int32_t 
                                      float* dispersion, float* best_value, float* best_solution,
                                      float* elites_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Sharded population, exchange over NVLink peer memory fused into the select / refit kernels (no reference counterpart;
+ * SURVEY.md section 8e "stretch": the gather issued from the kernel, and its threshold-first variant for large k).
+ * Every rank allocates a buffer of b200pets_peer_buffer_bytes(world, local_population, dims, elite_num) with
+ * b200pets_peer_alloc (cudaMalloc + its 64-byte cudaIpcMemHandle_t); ranks exchange the handles out of band and open each
+ * other's with b200pets_peer_open; peer_bufs [host] void*[world] = this process's pointer to every rank's buffer (its own
+ * included).  All ranks hold the same number of sequences (contiguous shards in rank order).  Per CEM iteration
+ * (epoch = 1, 2, 3, ... never reused, the same on all ranks):
+ *   b200pets_cem_values_push   NaN rule in place, this rank's values -> every rank's value table + flag
+ *   b200pets_cem_elites_refit  waits for all values, selects the global top elite_num (ties: lowest global index), sends the
+ *                              rows of the elites this rank owns to their (index-ordered) place in every rank's elite table,
+ *                              waits for all of them, refits (mu, dispersion, best) with the arithmetic of
+ *                              b200pets_cem_update (unbiased variance, sums in ascending global index order), then
+ *                              (sample_next != 0) draws this rank's next population shard like b200pets_cem_sample_shard.
+ *                              tag_word [dev] uint32 scratch. */
+size_t b200pets_peer_buffer_bytes(int32_t world, int32_t local_population, int32_t dims, int32_t elite_num);
+int b200pets_peer_alloc(size_t bytes, void** ptr, uint8_t* ipc_handle64);
+int b200pets_peer_open(const uint8_t* ipc_handle64, void** ptr);
+int b200pets_peer_close(void* ptr, int32_t owned);
+int b200pets_cem_values_push(int32_t local_population, int32_t dims, int32_t elite_num, float* values, int32_t rank,
+                             int32_t world, uint32_t epoch, void* const* peer_bufs, void* stream);
+int b200pets_cem_elites_refit(int32_t local_population, int32_t first_sequence, int32_t dims, int32_t elite_num,
+                              float alpha, int32_t use_std, int32_t rank, int32_t world, uint32_t epoch,
+                              void* const* peer_bufs, const float* population_in, float* mu, float* dispersion,
+                              float* best_value, float* best_solution, int32_t sample_next, const float* lower,
+                              const float* upper, uint64_t seed, uint64_t offset, int32_t clipped_normal,
+                              uint32_t* tag_word, float* population_out, void* stream);
+
 /* iCEM sampling (trajectory_opt.py:433-441 + util/math.py:318-396): coloured noise along the horizon from
  * N(0,1) draws sr, si [dev] float[n][A][H/2+1] (or NULL = Philox), scaled by sqrt(var) + mu and clipped. */
 int b200pets_icem_sample(int32_t n, int32_t horizon, int32_t act_dim, float exponent, const float* mu,

@@ -83,6 +83,15 @@ _SIGNATURES = {
     "b200pets_cem_plan_workspace_bytes": (C.c_size_t, [_P, C.POINTER(RolloutCfg), C.POINTER(CemCfg)]),
     "b200pets_cem_plan": (C.c_int, [_P, C.POINTER(RolloutCfg), C.POINTER(CemCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                     C.c_size_t, _P]),
+    "b200pets_peer_buffer_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "b200pets_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "b200pets_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "b200pets_peer_close": (C.c_int, [_P, C.c_int32]),
+    "b200pets_cem_values_push": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_uint32,
+                                           C.POINTER(C.c_void_p), _P]),
+    "b200pets_cem_elites_refit": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_uint32, C.POINTER(C.c_void_p), _P, _P, _P, _P, _P, C.c_int32, _P, _P,
+                                            C.c_uint64, C.c_uint64, C.c_int32, _P, _P, _P]),
     "b200pets_debug_timeline": (C.c_int, [_P]),
     "b200pets_debug_umma_bench": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "b200pets_selftest_umma": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P]),

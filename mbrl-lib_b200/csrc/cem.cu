@@ -4,6 +4,8 @@
 //   CEMOptimizer._sample_population 110-128, _update_population_params 130-140, optimize 142-188
 //   ICEMOptimizer.optimize 391-487;  util.math.truncated_normal_ util/math.py:69-92,
 //   powerlaw_psd_gaussian util/math.py:318-396;  TrajectoryOptimizer.optimize 563-567.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -516,6 +518,7 @@ cem_select_small_kernel(const SelArgs s, const float* __restrict__ row_totals, i
 // refit = 0: sample only (the first iteration's population); sample = 0: refit only (the last iteration).
 struct NextPop {
   int refit, sample;
+  int n_pop;  // sequences to draw (this rank's shard); the refit may run over a different number of rows (gathered records)
   const float* lb;
   const float* ub;
   const float* z;  // injected noise of the NEXT iteration or NULL
@@ -549,7 +552,7 @@ cem_refit_sample_kernel(const SelArgs s, const float* __restrict__ row_totals, i
     }
   }
   if (!q.sample) return;
-  const long long tot = (long long)s.n * s.dims;
+  const long long tot = (long long)q.n_pop * s.dims;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
     const int d = (int)(idx % s.dims);
     q.pop_out[idx] = cem_sample_element(idx, s.dims, __ldcg(s.mu + d), __ldcg(s.disp + d), q.lb[d], q.ub[d], q.z, q.seed, q.offset,
@@ -646,6 +649,237 @@ mppi_update_kernel(int n, int dims, float gamma, const float* __restrict__ pop, 
     float acc = 0.f;
     for (int w = 0; w < 32; ++w) acc += partial[w * dims + d];
     mean_out[d] = acc / sh_norm;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// Sharded population: the exchange of an iteration over NVLink peer memory, fused into the select / refit kernels (no
+// host-issued collective between them), and sized by the ELITE SET, not by rank count x elites:
+//   cem_values_push_kernel         NaN rule on this rank's values, then the values into slot `rank` of EVERY rank's value
+//                                  table (plain stores through the IPC mapping of the peer's buffer), system fence, epoch flag;
+//   cem_elites_refit_sample_kernel CTA 0: waits for all value flags -> every rank now holds all N values in global index order
+//                                  and runs the SAME radix select (k-th largest key, ties by lowest index) -> the rows of the
+//                                  elites that live on this rank go, with their values, to their position (ascending global
+//                                  index) in every rank's elite table -> epoch flag -> waits for all elite flags -> refit
+//                                  (mean / unbiased variance summed in ascending index order: the single-GPU arithmetic,
+//                                  bit for bit), best-so-far, tag; then every CTA draws this rank's next population shard.
+// Per rank and iteration: N * 4 B of values + (1 + dims) * 4 B per elite it owns, to each peer -- where gathering "the
+// local top-k of every rank" moves world x min(k, N / world) records and makes every rank select among them (at 8 ranks x
+// 500 sequences, k = 400: 3 200 records of 724 B and a second select, the limiter of weak scaling in round 2's first runs).
+// Two parities per table: a rank can be at most one iteration ahead of the slowest one.  Spins are bounded (~2 s) and
+// report through `status`.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerArgs {
+  int rank, world, n_loc, dims, elite_num, parity;
+  unsigned int epoch;
+  unsigned char* base[kMaxPeers];  // this process's mapping of rank p's buffer
+};
+
+__host__ __device__ inline size_t peer_al(size_t x) { return (x + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t peer_vals_bytes(int world, int n_loc) { return peer_al((size_t)world * n_loc * 4); }
+__host__ __device__ inline size_t peer_elite_bytes(int elite_num, int dims) { return peer_al((size_t)elite_num * (dims + 1) * 4); }
+__device__ __forceinline__ float* peer_vals(const PeerArgs& a, int p) {
+  return reinterpret_cast<float*>(a.base[p] + (size_t)a.parity * peer_vals_bytes(a.world, a.n_loc));
+}
+__device__ __forceinline__ float* peer_elites(const PeerArgs& a, int p) {
+  return reinterpret_cast<float*>(a.base[p] + 2 * peer_vals_bytes(a.world, a.n_loc) + (size_t)a.parity * peer_elite_bytes(a.elite_num, a.dims));
+}
+__device__ __forceinline__ unsigned int* peer_flags(const PeerArgs& a, int p, int phase) {  // [phase][parity][world]
+  return reinterpret_cast<unsigned int*>(a.base[p] + 2 * peer_vals_bytes(a.world, a.n_loc) + 2 * peer_elite_bytes(a.elite_num, a.dims)) +
+         ((size_t)phase * 2 + a.parity) * a.world;
+}
+__device__ __forceinline__ int* peer_status(const PeerArgs& a) {
+  return reinterpret_cast<int*>(reinterpret_cast<unsigned int*>(a.base[a.rank] + 2 * peer_vals_bytes(a.world, a.n_loc) +
+                                                                2 * peer_elite_bytes(a.elite_num, a.dims)) + 4 * a.world);
+}
+__device__ __forceinline__ void peer_signal(const PeerArgs& a, int phase) {  // after a system fence + barrier: threads 0..world-1
+  if (threadIdx.x < a.world) {
+    unsigned int* f = peer_flags(a, threadIdx.x, phase) + a.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.epoch) : "memory");
+  }
+}
+__device__ __forceinline__ void peer_wait(const PeerArgs& a, int phase) {  // threads 0..world-1 spin, then a barrier
+  if (threadIdx.x < a.world) {
+    const unsigned int* f = peer_flags(a, a.rank, phase) + threadIdx.x;
+    unsigned int v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v != a.epoch && clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
+        *peer_status(a) = 1 + phase * 100 + threadIdx.x;
+        break;
+      }
+    } while (v != a.epoch);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1) cem_values_push_kernel(float* __restrict__ values, const PeerArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  for (int i = threadIdx.x; i < a.n_loc; i += kSelThreads) {
+    float v = values[i];
+    if (isnan(v)) {  // trajectory_opt.py:178, in place like the reference
+      v = -1e-10f;
+      values[i] = v;
+    }
+    for (int p = 0; p < a.world; ++p) peer_vals(a, p)[(size_t)a.rank * a.n_loc + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  peer_signal(a, 0);
+}
+
+struct RefitArgs {
+  float alpha;
+  int use_std;
+  const float* pop;  // this rank's shard [n_loc][dims]
+  float *mu, *disp, *best_value, *best_solution;
+};
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+cem_elites_refit_sample_kernel(const PeerArgs a, const RefitArgs r, const NextPop q) {
+  extern __shared__ int my_pos[];  // [n_loc] position of my sequence in the ordered elite table, -1 if not an elite
+  __shared__ int hist[256];
+  __shared__ int warp_sums[32];
+  __shared__ int sh_total;
+  __shared__ uint32_t sh_prefix;
+  __shared__ int sh_krem;
+  __shared__ float sh_bv[32];
+  __shared__ int sh_bi[32];
+  pdl_trigger();
+  pdl_wait();
+  const int tid = threadIdx.x, dims = a.dims, k = a.elite_num;
+  if (blockIdx.x == 0) {
+    const int n = a.world * a.n_loc;
+    peer_wait(a, 0);
+    const float* vals = peer_vals(a, a.rank);
+    if (tid == 0) {
+      sh_prefix = 0;
+      sh_krem = k;
+    }
+    for (int i = tid; i < a.n_loc; i += kSelThreads) my_pos[i] = -1;
+    __syncthreads();
+    // ---- radix select of the k-th largest key, most significant byte first (as cem_select_kernel) ----
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int b = tid; b < 256; b += kSelThreads) hist[b] = 0;
+      __syncthreads();
+      const uint32_t prefix = sh_prefix;
+      const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (int i = tid; i < n; i += kSelThreads) {
+        const uint32_t key = order_key(__ldcg(vals + i));
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int krem = sh_krem, cum = 0, d = 255;
+        for (; d > 0; --d) {
+          if (cum + hist[d] >= krem) break;
+          cum += hist[d];
+        }
+        sh_krem = krem - cum;
+        sh_prefix = prefix | ((uint32_t)d << shift);
+      }
+      __syncthreads();
+    }
+    const uint32_t T = sh_prefix;
+    const int need_eq = sh_krem;
+    // ---- ordered positions (ascending global index); mine go into my_pos ----
+    const int lo = a.rank * a.n_loc, hi = lo + a.n_loc;
+    int base_sel = 0, base_eq = 0;
+    for (int c0 = 0; c0 < n; c0 += kSelThreads) {
+      const int i = c0 + tid;
+      const uint32_t key = i < n ? order_key(__ldcg(vals + i)) : 0u;
+      const int gt = (i < n && key > T) ? 1 : 0;
+      const int eq = (i < n && key == T) ? 1 : 0;
+      const int eq_rank = block_exclusive_scan(eq, warp_sums, &sh_total);
+      const int tot_eq = sh_total;
+      const int sel = gt | ((eq && (base_eq + eq_rank) < need_eq) ? 1 : 0);
+      const int pos = block_exclusive_scan(sel, warp_sums, &sh_total);
+      const int tot_sel = sh_total;
+      if (sel && i >= lo && i < hi) my_pos[i - lo] = base_sel + pos;
+      base_sel += tot_sel;
+      base_eq += tot_eq;
+      __syncthreads();
+    }
+    // ---- my elites -> their row of every rank's elite table: [value, sequence] ----
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int e = warp; e < a.n_loc; e += kSelThreads / 32) {
+      const int pos = my_pos[e];
+      if (pos < 0) continue;
+      const float v = __ldcg(vals + lo + e);
+      for (int p = 0; p < a.world; ++p) {
+        float* row = peer_elites(a, p) + (size_t)pos * (dims + 1);
+        if (lane == 0) row[0] = v;
+        for (int d = lane; d < dims; d += 32) row[1 + d] = r.pop[(size_t)e * dims + d];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    peer_signal(a, 1);
+    peer_wait(a, 1);
+    // ---- refit from the k ordered elite rows: the arithmetic of select_small_body ----
+    const float* el = peer_elites(a, a.rank);
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int e = tid; e < k; e += kSelThreads) {
+      const float v = __ldcg(el + (size_t)e * (dims + 1));
+      if (v > bv || (v == bv && e < bi)) { bv = v; bi = e; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sh_bv[warp] = bv; sh_bi[warp] = bi; }
+    __syncthreads();
+    bv = sh_bv[0]; bi = sh_bi[0];
+    for (int w = 1; w < kSelThreads / 32; ++w)
+      if (sh_bv[w] > bv || (sh_bv[w] == bv && sh_bi[w] < bi)) { bv = sh_bv[w]; bi = sh_bi[w]; }
+    const bool better = bv > *r.best_value;  // read before anybody writes it
+    __syncthreads();
+    for (int d = tid; d < dims; d += kSelThreads) {
+      float acc = 0.f;
+      for (int e = 0; e < k; ++e) acc += __ldcg(el + (size_t)e * (dims + 1) + 1 + d);
+      const float mean = acc / (float)k;
+      float acc2 = 0.f;
+      for (int e = 0; e < k; ++e) {
+        const float df = __ldcg(el + (size_t)e * (dims + 1) + 1 + d) - mean;
+        acc2 += df * df;
+      }
+      const float var = acc2 / (float)(k - 1);
+      const float nd = r.use_std ? sqrtf(var) : var;
+      r.mu[d] = r.alpha * r.mu[d] + (1.0f - r.alpha) * mean;
+      r.disp[d] = r.alpha * r.disp[d] + (1.0f - r.alpha) * nd;
+      if (better) r.best_solution[d] = __ldcg(el + (size_t)bi * (dims + 1) + 1 + d);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (better) *r.best_value = bv;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(q.flag), "r"(q.tag) : "memory");
+    }
+    __syncthreads();
+  } else {
+    if (tid == 0) {
+      unsigned int v;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q.flag) : "memory");
+      } while (v != q.tag && clock64() - t0 < 10000000000ll);
+    }
+    __syncthreads();
+  }
+  if (!q.sample) return;
+  const long long tot = (long long)q.n_pop * dims;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + tid; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % dims);
+    q.pop_out[idx] = cem_sample_element(idx, dims, __ldcg(r.mu + d), __ldcg(r.disp + d), q.lb[d], q.ub[d], q.z, q.seed, q.offset,
+                                        q.clipped, q.seq0);
   }
 }
 
@@ -746,6 +980,89 @@ int b200pets_cem_update_from_records(int32_t num_records, int32_t dims, int32_t 
                     workspace_bytes, stream);
 }
 
+// ---- peer-memory exchange of the sharded CEM (see cem_values_push_kernel) -----------------------------------------------
+size_t b200pets_peer_buffer_bytes(int32_t world, int32_t local_population, int32_t dims, int32_t elite_num) {
+  if (world <= 0 || local_population <= 0 || dims <= 0 || elite_num <= 0) return 0;
+  return 2 * peer_vals_bytes(world, local_population) + 2 * peer_elite_bytes(elite_num, dims) + peer_al((size_t)(4 * world + 1) * 4);
+}
+
+int b200pets_peer_alloc(size_t bytes, void** ptr, uint8_t* ipc_handle64) {
+  if (!ptr || !ipc_handle64 || bytes == 0) return b200pets_set_error(B200PETS_EINVAL, "peer_alloc: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaMalloc(ptr, bytes));
+  CUDA_TRY(cudaMemset(*ptr, 0, bytes));
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(ipc_handle64, &h, 64);
+  return B200PETS_OK;
+}
+
+int b200pets_peer_open(const uint8_t* ipc_handle64, void** ptr) {
+  if (!ptr || !ipc_handle64) return b200pets_set_error(B200PETS_EINVAL, "peer_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return B200PETS_OK;
+}
+
+int b200pets_peer_close(void* ptr, int32_t owned) {
+  if (!ptr) return B200PETS_OK;
+  if (owned) CUDA_TRY(cudaFree(ptr));
+  else CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return B200PETS_OK;
+}
+
+static int fill_peer_args(PeerArgs* a, int rank, int world, int n_loc, int dims, int elite_num, unsigned int epoch, void* const* peer_bufs) {
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !peer_bufs)
+    return b200pets_set_error(B200PETS_EINVAL, "peer exchange: need 1 <= world <= %d and the peers' buffers", kMaxPeers);
+  if (n_loc <= 0 || dims <= 0 || elite_num < 2 || elite_num > world * n_loc || epoch == 0)
+    return b200pets_set_error(B200PETS_EINVAL, "peer exchange: need 2 <= elite_num (%d) <= population (%d) and epoch > 0", elite_num, world * n_loc);
+  a->rank = rank; a->world = world; a->n_loc = n_loc; a->dims = dims; a->elite_num = elite_num;
+  a->epoch = epoch; a->parity = (int)(epoch & 1u);
+  for (int p = 0; p < world; ++p) {
+    if (!peer_bufs[p]) return b200pets_set_error(B200PETS_EINVAL, "peer exchange: buffer of rank %d missing", p);
+    a->base[p] = reinterpret_cast<unsigned char*>(peer_bufs[p]);
+  }
+  return B200PETS_OK;
+}
+
+int b200pets_cem_values_push(int32_t local_population, int32_t dims, int32_t elite_num, float* values, int32_t rank,
+                             int32_t world, uint32_t epoch, void* const* peer_bufs, void* stream) {
+  if (!values) return b200pets_set_error(B200PETS_EINVAL, "values_push: null argument");
+  PeerArgs a{};
+  int rc = fill_peer_args(&a, rank, world, local_population, dims, elite_num, epoch, peer_bufs);
+  if (rc) return rc;
+  CUDA_TRY(launch_pdl(cem_values_push_kernel, dim3(1), dim3(kSelThreads), 0, (cudaStream_t)stream, values, a));
+  return B200PETS_OK;
+}
+
+int b200pets_cem_elites_refit(int32_t local_population, int32_t first_sequence, int32_t dims, int32_t elite_num, float alpha,
+                              int32_t use_std, int32_t rank, int32_t world, uint32_t epoch, void* const* peer_bufs,
+                              const float* population_in, float* mu, float* dispersion, float* best_value,
+                              float* best_solution, int32_t sample_next, const float* lower, const float* upper,
+                              uint64_t seed, uint64_t offset, int32_t clipped_normal, uint32_t* tag_word,
+                              float* population_out, void* stream) {
+  if (!population_in || !mu || !dispersion || !best_value || !best_solution || !tag_word)
+    return b200pets_set_error(B200PETS_EINVAL, "elites_refit: null argument");
+  PeerArgs a{};
+  int rc = fill_peer_args(&a, rank, world, local_population, dims, elite_num, epoch, peer_bufs);
+  if (rc) return rc;
+  const size_t smem = (size_t)local_population * sizeof(int);
+  if (smem > 160 * 1024) return b200pets_set_error(B200PETS_EUNSUPPORTED, "elites_refit: more than 40 960 sequences per rank");
+  RefitArgs r{alpha, use_std, population_in, mu, dispersion, best_value, best_solution};
+  NextPop q{};
+  q.refit = 1; q.sample = sample_next; q.n_pop = local_population; q.lb = lower; q.ub = upper; q.z = nullptr;
+  q.seed = rng_key(seed, offset); q.offset = offset; q.clipped = clipped_normal; q.seq0 = first_sequence;
+  q.flag = tag_word; q.tag = epoch; q.pop_out = population_out;
+  const long long tot = (long long)local_population * dims;
+  unsigned grid = sample_next ? (unsigned)min((long long)64, (tot + kSelThreads - 1) / kSelThreads) : 1u;
+  if (grid < 1) grid = 1;
+  CUDA_TRY(cudaFuncSetAttribute(cem_elites_refit_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CUDA_TRY(launch_pdl(cem_elites_refit_sample_kernel, dim3(grid), dim3(kSelThreads), smem, (cudaStream_t)stream, a, r, q));
+  return B200PETS_OK;
+}
+
 int b200pets_icem_sample(int32_t n, int32_t horizon, int32_t act_dim, float exponent, const float* mu,
                          const float* var, const float* lower, const float* upper, const float* sr, const float* si,
                          uint64_t seed, uint64_t offset, float* population_out, void* stream) {
@@ -842,7 +1159,7 @@ int launch_cem_refit_sample(int population, int dims, int elite_num, float alpha
   s.partial = reinterpret_cast<float*>(workspace);
   s.elite_idx = reinterpret_cast<int*>(reinterpret_cast<float*>(workspace) + 33 * (size_t)dims);
   NextPop q{};
-  q.refit = refit; q.sample = sample; q.lb = lb; q.ub = ub; q.z = z_next; q.seed = seed; q.offset = offset;
+  q.refit = refit; q.sample = sample; q.n_pop = n; q.lb = lb; q.ub = ub; q.z = z_next; q.seed = seed; q.offset = offset;
   q.clipped = clipped; q.seq0 = seq0; q.flag = flag; q.tag = tag; q.pop_out = pop;
   const long long tot = (long long)n * dims;
   unsigned grid = sample ? (unsigned)min((long long)64, (tot + kSelThreads - 1) / kSelThreads) : 1u;

@@ -90,6 +90,72 @@ class ShardedCEMOptimizer:
         self.record_values = False
         self.last_values = None
         self.comm_events = None  # set to [] to record (start, end) CUDA events around every collective
+        # Exchange over NVLink peer memory fused into the select / refit kernels (b200pets_cem_values_push / _elites_refit:
+        # all values first, then only the rows of the global elites) instead of a host-issued NCCL all-gather of every
+        # rank's local top-k: set up lazily (needs dims), only for a real NCCL group on ONE node with equal shards.
+        # B200PETS_PEER_EXCHANGE=0 keeps the NCCL collective.
+        import os
+        self.peer_exchange = os.environ.get("B200PETS_PEER_EXCHANGE", "1") != "0" and gather is None
+        self._peer = None  # {"own": ptr, "ptrs": (c_void_p * world), "key": (k, dims), "tag": tensor}
+        self._epoch = 0
+
+    # ---- peer-memory gather buffers ---------------------------------------------------------------------------
+    def _setup_peers(self, dims: int):
+        import socket
+
+        if not self.peer_exchange or self.world < 2 or self.world > 16 or not dist.is_initialized():
+            return None
+        if dist.get_backend(self.group) != "nccl":
+            return None
+        key = (self.local_population, dims)
+        if self._peer is not None and self._peer["key"] == key:
+            return self._peer
+        if self._peer is not None:
+            self._close_peers()
+        if self.population_size % self.world != 0 or self.local_population > 40960 or self.elite_num < 2:
+            self.peer_exchange = False  # unequal shards / very large shards: keep the collective
+            return None
+        nbytes = self.lib.b200pets_peer_buffer_bytes(self.world, self.local_population, dims, self.elite_num)
+        own, handle = C.c_void_p(), C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200pets_peer_alloc(nbytes, C.byref(own), handle), "peer_alloc")
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (socket.gethostname(), bytes(handle.raw)), group=self.group)
+        ptrs = (C.c_void_p * self.world)()
+        if len({h for h, _ in infos}) != 1:  # peers on another node: IPC handles do not travel
+            with torch.cuda.device(self.device):
+                self.lib.b200pets_peer_close(own, 1)
+            self.peer_exchange = False
+            return None
+        with torch.cuda.device(self.device):
+            for r, (_, hb) in enumerate(infos):
+                if r == self.rank:
+                    ptrs[r] = own.value
+                else:
+                    q = C.c_void_p()
+                    _lib.check(self.lib.b200pets_peer_open(hb, C.byref(q)), "peer_open")
+                    ptrs[r] = q.value
+        dist.barrier(group=self.group)
+        self._peer = {"own": own, "ptrs": ptrs, "key": key,
+                      "tag": torch.zeros(1, dtype=torch.int32, device=self.device)}
+        return self._peer
+
+    def _close_peers(self):
+        if self._peer is None:
+            return
+        try:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                for r in range(self.world):
+                    if r != self.rank and self._peer["ptrs"][r]:
+                        self.lib.b200pets_peer_close(C.c_void_p(self._peer["ptrs"][r]), 0)
+                self.lib.b200pets_peer_close(self._peer["own"], 1)
+        except Exception:
+            pass
+        self._peer = None
+
+    def __del__(self):
+        self._close_peers()
 
     def _buffers(self, shape):
         dims = int(np.prod(shape))
@@ -145,13 +211,15 @@ class ShardedCEMOptimizer:
         else:
             call = self._offset
             seed = self._seed
+        peer = self._setup_peers(dims)
         with torch.cuda.device(dev):
             stream = _lib.stream_ptr()
             for i in range(self.num_iterations):
                 off = call * 1024 + i
-                _lib.check(self.lib.b200pets_cem_sample_shard(
-                    n_loc, self.local_offset, dims, _lib.ptr(mu), _lib.ptr(disp), _lib.ptr(self.lower_bound),
-                    _lib.ptr(self.upper_bound), None, seed, off, 0, _lib.ptr(pop), stream), "cem_sample_shard")
+                if peer is None or i == 0:  # (peer path: later populations are drawn by the refit kernel)
+                    _lib.check(self.lib.b200pets_cem_sample_shard(
+                        n_loc, self.local_offset, dims, _lib.ptr(mu), _lib.ptr(disp), _lib.ptr(self.lower_bound),
+                        _lib.ptr(self.upper_bound), None, seed, off, 0, _lib.ptr(pop), stream), "cem_sample_shard")
                 if fused is not None:  # ModelEnv objective: one C call, no per-iteration host staging
                     rcfg.offset = off
                     _lib.check(self.lib.b200pets_eval_sequences(env.staged.handle, C.byref(rcfg), _lib.ptr(obs0), _lib.ptr(pop), None,
@@ -163,6 +231,26 @@ class ShardedCEMOptimizer:
                     callback(pop, values, i)
                 if self.record_values:
                     self.last_values[i].copy_(values)
+                if peer is not None:
+                    # values -> every rank over NVLink + flag; the refit kernel waits for them, selects the GLOBAL elites, ships
+                    # the rows this rank owns, waits for everybody's, refits and draws the next shard: two launches after the
+                    # rollout and no host-issued collective on the iteration's critical path
+                    self._epoch += 1
+                    if self.comm_events is not None:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                    _lib.check(self.lib.b200pets_cem_values_push(n_loc, dims, self.elite_num, _lib.ptr(values), self.rank, self.world,
+                                                                 self._epoch, peer["ptrs"], stream), "cem_values_push")
+                    more = 1 if i + 1 < self.num_iterations else 0
+                    _lib.check(self.lib.b200pets_cem_elites_refit(
+                        n_loc, self.local_offset, dims, self.elite_num, float(self.alpha), 0, self.rank, self.world, self._epoch,
+                        peer["ptrs"], _lib.ptr(pop), _lib.ptr(mu), _lib.ptr(disp), _lib.ptr(best_val), _lib.ptr(best_sol), more,
+                        _lib.ptr(self.lower_bound), _lib.ptr(self.upper_bound), seed, call * 1024 + i + 1, 0, _lib.ptr(peer["tag"]),
+                        _lib.ptr(pop), stream), "cem_elites_refit")
+                    if self.comm_events is not None:  # (exchange + select + refit + next population: the waits are in here)
+                        e1.record()
+                        self.comm_events.append((e0, e1))
+                    continue
                 _lib.check(self.lib.b200pets_cem_local_topk(n_loc, dims, k, _lib.ptr(pop), _lib.ptr(values), _lib.ptr(records),
                                                             _lib.ptr(ws), nbytes, stream), "cem_local_topk")
                 if self.comm_events is not None:

@@ -31,7 +31,10 @@ def main():
     lb, ub = np.full((H, A), spec.action_lb).tolist(), np.full((H, A), spec.action_ub).tolist()
     inp = syn.make_rollout_inputs(spec, with_noise=False)
     out = {}
-    for precision in ("bf16_tc", "f32"):
+    for precision, peer_mode in (("bf16_tc", "1"), ("f32", "1"), ("bf16_tc", "0")):
+        # peer_mode 1: records exchanged over NVLink peer memory by the top-k kernel itself; 0: NCCL all-gather
+        os.environ["B200PETS_PEER_EXCHANGE"] = peer_mode
+
         def make_env():
             model = bp.model_from_arrays(spec, arrays, dev)
             return bp.ModelEnv(tp._Env(spec), model, functions.TERM_FNS[spec.term_fn], functions.REWARD_FNS[spec.reward_fn],
@@ -43,6 +46,9 @@ def main():
         opt.record_values = True
         sol = opt.optimize(_FusedObjective(env, inp["obs0"], P), x0=torch.zeros(H, A, device=dev))
         torch.cuda.synchronize()
+        used_peers = opt._peer is not None
+        if peer_mode == "1" and not used_peers:
+            raise RuntimeError("peer exchange was not set up on a single-node NCCL group")
         # every rank holds the same plan without a broadcast
         gathered = [torch.empty_like(sol) for _ in range(world)]
         dist.all_gather(gathered, sol)
@@ -58,7 +64,7 @@ def main():
             torch.cuda.synchronize()
             union = torch.cat(vals, dim=1)
             ok_ref = bool(torch.equal(union, ref_opt.last_values)) and bool(torch.equal(ref, sol))
-            out[precision] = {"ranks_agree": same, "equals_single_gpu_plan": ok_ref,
+            out[f"{precision}_{'peer' if used_peers else 'nccl'}"] = {"ranks_agree": same, "equals_single_gpu_plan": ok_ref,
                               "max_abs_diff_plan": float((ref - sol).abs().max()),
                               "max_abs_diff_values": float((union - ref_opt.last_values).abs().max())}
         flag = torch.tensor([int(same and ok_ref)], device=dev)
