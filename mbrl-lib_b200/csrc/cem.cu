@@ -423,6 +423,8 @@ static __device__ __forceinline__ void select_small_body(const SelArgs& s, const
   __shared__ unsigned char sf[kSmallN];
   __shared__ int eidx[kSmallN];
   __shared__ int sh_best;
+  __shared__ int sel_warp_sums[32];
+  __shared__ int sel_total;
   const int tid = threadIdx.x;
   const int n = s.n, k = s.k, dims = s.dims;
   for (int i = tid; i < n; i += kSelThreads) {
@@ -441,26 +443,40 @@ static __device__ __forceinline__ void select_small_body(const SelArgs& s, const
   }
   if (tid == 0) sh_best = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += kSelThreads) {
-    const float vi = sv[i];
+  // rank by counting (vj > vi, ties -> lower index first); T threads share one candidate's n comparisons (500 sequences: 2)
+  int T = 1;
+  while (T < 32 && 2 * T * n <= kSelThreads) T *= 2;
+  for (int base = 0; base < n; base += kSelThreads / T) {
+    const int i = base + tid / T, part = tid % T;  // T divides 32: the partners of a candidate sit in one warp
     int rank = 0;
-    for (int j = 0; j < n; ++j) {
-      const float vj = sv[j];
-      rank += (vj > vi || (vj == vi && j < i)) ? 1 : 0;
+    if (i < n) {
+      const float vi = sv[i];
+      for (int j = part; j < n; j += T) {
+        const float vj = sv[j];
+        rank += (vj > vi || (vj == vi && j < i)) ? 1 : 0;
+      }
     }
-    sf[i] = rank < k ? 1 : 0;
-    if (rank == 0) sh_best = i;  // the maximum, lowest index on ties
-  }
-  __syncthreads();
-  for (int i = tid; i < n; i += kSelThreads) {
-    if (sf[i]) {
-      int pos = 0;
-      for (int j = 0; j < i; ++j) pos += sf[j];
-      eidx[pos] = i;
-      s.elite_idx[pos] = i;
+    for (int o = T >> 1; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (i < n && part == 0) {
+      sf[i] = rank < k ? 1 : 0;
+      if (rank == 0) sh_best = i;  // the maximum, lowest index on ties
     }
   }
   __syncthreads();
+  {  // ascending positions of the selected indices: block-wide exclusive scan of the flags
+    int base_sel = 0;
+    for (int c0 = 0; c0 < n; c0 += kSelThreads) {
+      const int i = c0 + tid;
+      const int flag = i < n ? (int)sf[i] : 0;
+      const int pos = block_exclusive_scan(flag, sel_warp_sums, &sel_total);
+      if (flag) {
+        eidx[base_sel + pos] = i;
+        s.elite_idx[base_sel + pos] = i;
+      }
+      base_sel += sel_total;
+      __syncthreads();
+    }
+  }
   for (int idx = tid; idx < k * dims; idx += kSelThreads) {
     const int e = idx / dims, d = idx - e * dims;
     esm[idx] = s.pop[eidx[e] * s.pstride + d];
