@@ -176,6 +176,138 @@ def mbpo_step_extra(device, flush):
             "flop_per_transition": 263600}
 
 
+def build_problem_variant(device, workload, **over):
+    """build_problem for a synthetic case with some fields replaced (population / horizon / particles of a BASELINE config)."""
+    import dataclasses
+
+    import mbrl_lib_b200 as bp
+    from mbrl_lib_b200 import functions
+
+    spec = dataclasses.replace(syn.CASES[workload], **over)
+    arrays = syn.make_model_arrays(spec)
+    model = bp.model_from_arrays(spec, arrays, device)
+
+    class _Env:
+        observation_space = _Box(-np.inf, np.inf, spec.obs_dim)
+        action_space = _Box(spec.action_lb, spec.action_ub, spec.act_dim)
+
+    rew = functions.REWARD_FNS[spec.reward_fn] if spec.reward_fn else None
+    env = bp.ModelEnv(_Env(), model, functions.TERM_FNS[spec.term_fn], rew,
+                      generator=torch.Generator(device=device).manual_seed(0), precision="auto", ts1="tile_shuffle")
+    return spec, arrays, env
+
+
+def config3_icem_extra(device, flush, peak_tf):
+    """BASELINE config 3: PETS Humanoid-v4 with iCEM (pop 1000, decay 1.3, coloured noise beta 2, keep 0.3, 5 iterations, H 40,
+    20 particles; conf pets_icem_cartpole.yaml values) through ICEMOptimizer.optimize over evaluate_action_sequences.
+    Two model shapes: the truncated-observation Humanoid (obs 45: inside the tensor-core plan) and the real Humanoid-v4
+    dims (obs 376, in 393 -> out 754: outside it, served by the fp32 kernel).  Algorithmic FLOP per sequence = 2 sum K N x P x H."""
+    import mbrl_lib_b200 as bp
+
+    rows = []
+    for name, reps in (("humanoid_trunc", 5), ("humanoid_v4", 2)):
+        spec, _, env = build_problem_variant(device, name, population=1000, horizon=40, particles=20)
+        H, A, P = spec.horizon, spec.act_dim, spec.particles
+        lb, ub = np.full((H, A), spec.action_lb).tolist(), np.full((H, A), spec.action_ub).tolist()
+        opt = bp.ICEMOptimizer(5, 0.1, 1000, 1.3, 2.0, lb, ub, 0.3, 0.1, device, return_mean_elites=True, population_size_module=5)
+        obs0 = syn.make_rollout_inputs(spec, with_noise=False)["obs0"]
+        seqs = {"n": 0}
+
+        def obj(pop):
+            seqs["n"] += pop.shape[0]
+            return env.evaluate_action_sequences(pop, obs0, P)
+
+        x0 = torch.zeros(H, A, device=device)
+        opt.optimize(obj, x0=x0)
+        torch.cuda.synchronize()
+        seqs["n"] = 0
+        ms = time_events(lambda: opt.optimize(obj, x0=x0), reps, flush)
+        per_plan = seqs["n"] / reps
+        dims = [(spec.in_size, spec.hid_size)] + [(spec.hid_size, spec.hid_size)] * (spec.num_layers - 1) + [(spec.hid_size, 2 * spec.out_size)]
+        flop_seq = 2.0 * sum(k * n for k, n in dims) * P * H
+        sps = per_plan / (ms * 1e-3)
+        rows.append({"model": name, "obs_dim": spec.obs_dim, "in": spec.in_size, "out": 2 * spec.out_size, "kernel": env.precision,
+                     "sequences_per_plan": per_plan, "ms_per_plan": ms, "sequences_per_s": sps,
+                     "algorithmic_mflop_per_sequence": flop_seq / 1e6,
+                     "tensor_roofline_frac": sps * flop_seq / 1e12 / peak_tf if env.precision == "bf16_tc" else None,
+                     "tflops": sps * flop_seq / 1e12})
+    return {"workload": "PETS Humanoid iCEM: pop 1000 decaying by 1.3, 5 iterations, H 40, 20 particles, coloured noise beta 2, "
+                        "keep_elite_frac 0.3 (ICEMOptimizer.optimize over evaluate_action_sequences, CUDA events per plan)",
+            "rows": rows}
+
+
+def config4_mbpo_loop_extra(device):
+    """BASELINE config 4 as MBPO runs it (mbrl/algorithms/mbpo.py:31-63): 100 000 start states x k model steps with an actor
+    between the steps, transitions into a SAC buffer.  Device loop (mbpo.rollout_model_and_populate_sac_buffer: states,
+    predictions and the accum_dones mask stay in HBM, one D2H of the compacted transitions) vs the reference-shaped numpy
+    loop over ModelEnv.step (per-step H2D / D2H and host masking).  The actor is a fixed tanh-linear map (a torch callable on
+    the device in the first case, numpy in the second)."""
+    from mbrl_lib_b200 import mbpo
+
+    spec, _, env = build_problem(device, "mbpo_halfcheetah")
+    B, k = 100000, 5
+    inp = syn.make_step_inputs(spec, B)
+    W = torch.from_numpy(np.random.default_rng(0).standard_normal((spec.obs_dim, spec.act_dim)).astype(np.float32) * 0.3).to(device)
+    Wh = W.cpu().numpy()
+
+    class _Batch:
+        def astuple(self):
+            return (inp["obs"], None, None, None, None, None)
+
+    class _Replay:
+        def sample(self, n):
+            return _Batch()
+
+    class _Sac:
+        rows = 0
+
+        def add_batch(self, obs, action, next_obs, reward, terminated, truncated):
+            _Sac.rows += len(obs)
+
+    class _TorchAgent:
+        def act_torch(self, obs, sample):
+            return torch.tanh(obs @ W)
+
+    class _NumpyAgent:
+        def act(self, obs, sample=False, batched=False):
+            return np.tanh(obs @ Wh).astype(np.float32)
+
+    def device_loop():
+        mbpo.rollout_model_and_populate_sac_buffer(env, _Replay(), _TorchAgent(), _Sac(), True, k, B)
+
+    def numpy_loop():  # the reference's loop body over our ModelEnv.step (numpy in, numpy out, every step)
+        agent = _NumpyAgent()
+        sac = _Sac()
+        model_state = env.reset(inp["obs"], return_as_np=True)
+        accum = np.zeros(B, dtype=bool)
+        obs = inp["obs"]
+        for _ in range(k):
+            action = agent.act(obs, sample=True, batched=True)
+            pred_next, pred_rew, pred_done, model_state = env.step(action, model_state, sample=True)
+            keep = ~accum
+            sac.add_batch(obs[keep], action[keep], pred_next[keep], pred_rew[keep, 0], pred_done[keep, 0], np.zeros(keep.sum(), bool))
+            obs = pred_next
+            accum |= pred_done.squeeze()
+
+    out = {}
+    for name, fn in (("device_loop", device_loop), ("numpy_loop", numpy_loop)):
+        fn()
+        torch.cuda.synchronize()
+        _Sac.rows = 0
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        out[name + "_ms"] = dt * 1e3
+        out[name + "_transitions_per_s"] = _Sac.rows / reps / dt
+    out["workload"] = f"MBPO HalfCheetah model rollouts: {B} start states x {k} steps, actor between steps, transitions to a SAC buffer (host wall clock)"
+    out["pcie_bytes_numpy_loop_per_step"] = B * ((spec.obs_dim + spec.act_dim) * 4 + (spec.obs_dim + 1) * 4 + 1)
+    out["pcie_bytes_device_loop_total"] = B * spec.obs_dim * 4 + k * B * ((2 * spec.obs_dim + spec.act_dim + 1) * 4 + 1)
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     import mbrl_lib_b200 as bp
@@ -331,6 +463,12 @@ def run_ours(args):
             del big
         extras["population_scan_rollout_only"] = scan
         extras["config4_mbpo_step"] = mbpo_step_extra(device, flush)
+        for key, fn in (("config3_humanoid_icem", lambda: config3_icem_extra(device, flush, peak_tf)),
+                        ("config4_mbpo_rollout_loop", lambda: config4_mbpo_loop_extra(device))):
+            try:  # extra lines must never take the headline measurement down with them
+                extras[key] = fn()
+            except Exception as exc:  # pragma: no cover - depends on the box
+                extras[key] = {"error": f"{type(exc).__name__}: {exc}"}
     # ---- config 5: fixed GLOBAL population sharded over the ranks (strong scaling), collective share of an iteration ----
     if world > 1 and not args.no_scan5:
         from mbrl_lib_b200.dist import ShardedCEMOptimizer
