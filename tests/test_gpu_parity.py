@@ -150,10 +150,17 @@ def test_rollout_tc_discrete_rewards(golden_dir, name):
     inp = syn.make_rollout_inputs(spec)
     got = gpu_returns(env, spec, inp)
     gold = np.load(os.path.join(golden_dir, f"rollout_{name}.npz"))
+    # against the oracle run with bf16-rounded operands the discrete outcomes must agree (measured: 0 of the sequences differ,
+    # mean |diff| <= 2.2e-6, tests/prof_tolerances.py) ...
+    orc = oracle_returns(spec, arrays, inp, bf16=True)
+    d_o = np.abs(got - orc)
+    assert (d_o > 1e-2 * np.maximum(1.0, np.abs(orc))).mean() <= 0.01
+    assert d_o.mean() <= 1e-4 * max(1.0, float(np.abs(orc).mean()))
+    # ... and against the fp32 golden only a state near a termination threshold may flip (measured: 3 % of cartpole's
+    # sequences, none elsewhere; mean |diff| <= 1.5e-3)
     diff = np.abs(got - gold["returns"])
-    # bf16 operands move states near a termination threshold more often than fp32 summation order does
-    assert (diff > 1e-2 * np.maximum(1.0, np.abs(gold["returns"]))).mean() <= 0.15
-    assert np.abs(got.mean() - gold["returns"].mean()) <= 0.05 * max(1.0, np.abs(gold["returns"]).mean())
+    assert (diff > 1e-2 * np.maximum(1.0, np.abs(gold["returns"]))).mean() <= 0.06
+    assert diff.mean() <= 5e-3 * max(1.0, np.abs(gold["returns"]).mean())
 
 
 @pytest.mark.parametrize("precision,tol", [("f32", 2e-4), ("bf16_tc", 2e-2)])
@@ -274,7 +281,7 @@ def test_mppi_optimizer_matches_reference(golden_dir):
         np.testing.assert_allclose(sol.cpu().numpy(), g[f"sol{call}"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("precision,tol", [("f32", 5e-4), ("bf16_tc", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("f32", 5e-4), ("bf16_tc", 2e-3)])
 def test_fused_cem_plan_matches_reference(golden_dir, precision, tol):
     """CEMOptimizer.optimize over ModelEnv.evaluate_action_sequences as ONE C call, injected noise."""
     import mbrl_lib_b200 as bp
@@ -302,7 +309,9 @@ def test_fused_cem_plan_matches_reference(golden_dir, precision, tol):
         assert np.abs(vals - g["values"]).max() <= tol * scale
         np.testing.assert_allclose(sol.cpu().numpy(), g["solution"], rtol=1e-3, atol=1e-3)
     else:
-        assert np.abs(sol.cpu().numpy() - g["solution"]).max() <= 0.1  # elite membership may flip at bf16
+        assert np.abs(vals - g["values"]).max() <= tol * scale  # measured 2.1e-4 of scale (tests/prof_tolerances.py)
+        # elite membership did not flip on this case (measured max |diff| 1.2e-7); a flip would move the mean by ~1e-2
+        assert np.abs(sol.cpu().numpy() - g["solution"]).max() <= 1e-3
 
 
 def test_fused_iteration_kernel_equals_multi_kernel_plan():
