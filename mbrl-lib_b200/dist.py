@@ -115,26 +115,44 @@ class ShardedCEMOptimizer:
         if self.population_size % self.world != 0 or self.local_population > 40960 or self.elite_num < 2:
             self.peer_exchange = False  # unequal shards / very large shards: keep the collective
             return None
+        # Every decision below is taken from information ALL ranks hold (gathered tuples), so that either every rank uses the
+        # peer path or none does: a rank that cannot allocate / map a buffer makes everybody fall back to the NCCL collective.
         nbytes = self.lib.b200pets_peer_buffer_bytes(self.world, self.local_population, dims, self.elite_num)
-        own, handle = C.c_void_p(), C.create_string_buffer(64)
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.b200pets_peer_alloc(nbytes, C.byref(own), handle), "peer_alloc")
-        infos = [None] * self.world
-        dist.all_gather_object(infos, (socket.gethostname(), bytes(handle.raw)), group=self.group)
-        ptrs = (C.c_void_p * self.world)()
-        if len({h for h, _ in infos}) != 1:  # peers on another node: IPC handles do not travel
+        own, handle, ok = C.c_void_p(), C.create_string_buffer(64), True
+        try:
             with torch.cuda.device(self.device):
-                self.lib.b200pets_peer_close(own, 1)
+                _lib.check(self.lib.b200pets_peer_alloc(nbytes, C.byref(own), handle), "peer_alloc")
+        except Exception:
+            ok, own = False, C.c_void_p()
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (socket.gethostname(), bytes(handle.raw), ok), group=self.group)
+        opened = []
+        if all(i[2] for i in infos) and len({i[0] for i in infos}) == 1:  # (another node: IPC handles do not travel)
+            ptrs = (C.c_void_p * self.world)()
+            try:
+                with torch.cuda.device(self.device):
+                    for r, (_, hb, _) in enumerate(infos):
+                        if r == self.rank:
+                            ptrs[r] = own.value
+                        else:
+                            q = C.c_void_p()
+                            _lib.check(self.lib.b200pets_peer_open(hb, C.byref(q)), "peer_open")
+                            opened.append(q)
+                            ptrs[r] = q.value
+            except Exception:
+                ok = False
+        else:
+            ok = False
+        oks = [None] * self.world
+        dist.all_gather_object(oks, ok, group=self.group)
+        if not all(oks):
+            with torch.cuda.device(self.device):
+                for q in opened:
+                    self.lib.b200pets_peer_close(q, 0)
+                if own.value:
+                    self.lib.b200pets_peer_close(own, 1)
             self.peer_exchange = False
             return None
-        with torch.cuda.device(self.device):
-            for r, (_, hb) in enumerate(infos):
-                if r == self.rank:
-                    ptrs[r] = own.value
-                else:
-                    q = C.c_void_p()
-                    _lib.check(self.lib.b200pets_peer_open(hb, C.byref(q)), "peer_open")
-                    ptrs[r] = q.value
         dist.barrier(group=self.group)
         self._peer = {"own": own, "ptrs": ptrs, "key": key,
                       "tag": torch.zeros(1, dtype=torch.int32, device=self.device)}
