@@ -6,8 +6,10 @@
 //    epilogue warps as bf16 pairs with tcgen05.st into a TMEM buffer and never touch shared memory;
 //  * the B operand (weights) is streamed from the L2-resident packed image into two shared-memory layer slots by
 //    1-D TMA bulk copies (cp.async.bulk + mbarrier expect_tx), one slot in use while the next layer is in flight;
-//  * hidden layers are split in two N halves so that epilogue, MMAs of the other half and the next layer's first
-//    K steps overlap (see the kernel's header comment).
+//  * hidden layers are split in two N halves (128 + 80 columns at width 208) so that epilogue, MMAs of the other half
+//    and the next layer's first K steps overlap (see the kernel's header comment);
+//  * without an observation pre-processor the output-layer epilogue also writes the next step's layer-0 operand
+//    (no barrier, no builder pass between two steps); propagation "expectation" runs M member passes per step.
 //
 // Warp roles (64 + 128 * CS threads):  warp 0 = weight producer (one elected lane),
 //                            warp 1 = TMEM allocator + MMA issuer (converged warp, MMAs under elect.sync),
@@ -269,8 +271,11 @@ static __device__ __noinline__ void cem_tail_refit(const TailArgs* ap, int dims,
 // Hidden layers are split in two N halves so that the epilogue of half 0 runs under the MMAs of half 1, and the next
 // layer's first K steps (which only read half 0's activations) run under the epilogue of half 1:
 //
-//   MMA   : [l.h0 K0-6][l.h0 K7-12] [l.h1 K0-12]        [l+1.h0 K0-6] ..wait.. [l+1.h0 K7-12][l+1.h1 ...
-//   EPI   :                         [epi l.h0 -> A' cols 0-111]  [epi l.h1 -> A' cols 112-207]  [epi l+1.h0 ...
+//   (width 208 = 13 chunks of 16 columns; half 0 = 8 chunks = 128 columns, half 1 = 5 chunks incl. the short tail chunk)
+//   MMA   : [l.h0 K0-7][l.h0 K8-12] [l.h1 K0-12]        [l+1.h0 K0-7] ..wait.. [l+1.h0 K8-12][l+1.h1 ...
+//   EPI   :                         [epi l.h0 -> A' cols 0-127]  [epi l.h1 -> A' cols 128-207]  [epi l+1.h0 ...
+// An MMA costs max(65, N / 2) cycles per K step (profiles/r2_umma_issue_rate_ts.txt): 128 + 80 columns is the cheapest
+// two-way split, and finer splits / per-round issue schedules measured slower (wip/0003).
 //
 // TMEM columns: [0, 256) accumulators (hidden: halves at 0 and h0n; output layer at 0), [256, 384) and [384, 512)
 // the two activation buffers (layer g reads buffer g & 1 and its epilogue writes buffer (g + 1) & 1).
