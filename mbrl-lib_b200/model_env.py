@@ -144,13 +144,21 @@ class ModelEnv:
 
         def _wrap(obj, name):
             fn = getattr(obj, name, None)
-            if fn is None or getattr(fn, "_b200pets_pushes", False):
+            if fn is None:
                 return
+            if getattr(fn, "_b200pets_pushes", False):  # already wrapped (another ModelEnv of the same model): join its list
+                if all(e is not env for e in fn._b200pets_envs):
+                    fn._b200pets_envs.append(env)
+                return
+            envs = [env]
+
             def pushed(*a, **kw):
                 out = fn(*a, **kw)
-                env.staged.ensure_fresh()
+                for e in envs:
+                    e.staged.ensure_fresh()
                 return out
             pushed._b200pets_pushes = True
+            pushed._b200pets_envs = envs
             pushed.__wrapped__ = fn
             setattr(obj, name, pushed)
 

@@ -189,3 +189,49 @@ def test_rollout_model_env_protocol():
     assert [o.min() for o in obs] == list(range(L + 1))
     obs, _, _ = rollout_model_env(env, np.zeros(D), 3 * agent.seq, None, num_samples=S)
     assert [o.max() for o in obs] == [3 * i for i in range(L + 1)]
+
+
+def test_hand_off_wrappers_push_every_registered_env():
+    """ModelEnv.hand_off_from: wrapping is idempotent per object and serves several environments of one model (CPU: the
+    environments are bare objects with a counting stand-in for the staged copy; the GPU test runs the reference's trainer)."""
+    from mbrl_lib_b200.model_env import ModelEnv
+
+    class _Staged:
+        def __init__(self):
+            self.n = 0
+
+        def ensure_fresh(self):
+            self.n += 1
+
+    class _Model:
+        def __init__(self):
+            self.calls = []
+
+        def update_normalizer(self, batch):
+            self.calls.append("norm")
+
+        def set_elite(self, idx):
+            self.calls.append("elite")
+
+    class _Trainer:
+        def train(self, *a, **kw):
+            return "losses"
+
+    def bare_env(model):
+        e = ModelEnv.__new__(ModelEnv)
+        e.dynamics_model, e.staged, e._auto_refresh = model, _Staged(), True
+        return e
+
+    model, trainer = _Model(), _Trainer()
+    e1, e2 = bare_env(model), bare_env(model)
+    assert e1.hand_off_from(trainer) is trainer and e1._auto_refresh is False and e1.staged.n == 1
+    e1.hand_off_from(trainer)  # again: no second layer of wrappers
+    e2.hand_off_from(trainer)
+    n1, n2 = e1.staged.n, e2.staged.n
+    assert trainer.train("data") == "losses"
+    assert (e1.staged.n, e2.staged.n) == (n1 + 1, n2 + 1), "one push per environment and call"
+    model.update_normalizer(None)
+    model.set_elite([0])
+    assert model.calls == ["norm", "elite"] and (e1.staged.n, e2.staged.n) == (n1 + 3, n2 + 3)
+    e1._fresh()  # the hot path no longer polls
+    assert e1.staged.n == n1 + 3
